@@ -1,0 +1,625 @@
+// C-ABI layer of the fastMPC hot path (include/fmpc.h): argument validation with the reference's
+// error() semantics, host-side precompute of the iterate-independent Schur blocks, device buffers,
+// the MATLAB default random stream, and the batched entry points.  No CPU fallback: every compute
+// entry point fails with FMPC_ERR_CUDA when no sm_100 device is usable.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "../../include/fmpc.h"
+#include "fmpc_internal.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// MATLAB's default global stream: MT19937 seeded with 5489, doubles from genrand_res53
+// (`rand` in inf_newton_solver.m:2).
+// ---------------------------------------------------------------------------------------------
+struct MT19937 {
+    uint32_t mt[624];
+    int idx;
+    explicit MT19937(uint32_t seed = 5489u) { reseed(seed); }
+    void reseed(uint32_t seed)
+    {
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next32()
+    {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; ++i) {
+                uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    double rand53()
+    {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+};
+
+#define CU_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { last_cuda_error = e_; return FMPC_ERR_CUDA; } } while (0)
+thread_local cudaError_t last_cuda_error = cudaSuccess;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        if (cudaMalloc(&p, need) != cudaSuccess) return -1;
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+bool is_diag(const double *A, int n)
+{
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i)
+            if (i != j && A[(size_t)j * n + i] != 0.0) return false;
+    return true;
+}
+
+} // namespace
+
+struct fmpc_handle {
+    int device = 0;
+    int n = 0, m = 0, T = 0, var_order = 2, max_batch = 0;
+    DevSys S{};
+    SolveLaunchCfg cfg{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> sys_allocs;       // problem-constant device arrays
+    DevBuf ws, counters;                  // per-CTA scratch; {counter u32 (pad), iters_total u64}
+    // staging for the host-pointer entry points
+    DevBuf d_x0, d_x0pre, d_uprev, d_w, d_xf, d_X, d_U, d_nu0, d_status, d_iters;
+    // closed-loop state
+    DevBuf d_a, d_Uacc, d_Xacc, d_itacc;
+    MT19937 rng;
+    long long launches = 0;
+    size_t ws_stride = 0;
+    std::vector<double> h_nu;             // host staging for generated nu0
+};
+
+namespace {
+
+template <class T> T *upload(fmpc_handle *h, const std::vector<T> &v)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, v.size() * sizeof(T) + 16) != cudaSuccess) return nullptr;
+    if (!v.empty() && cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(p); return nullptr; }
+    h->sys_allocs.push_back(p);
+    return (T *)p;
+}
+
+// Builds the iterate-independent blocks of Y = C inv(Phi) C' (row-major n x n) for diagonal Q/Qf:
+//   Y[i,i]   = B Rt_i^-1 B' (iterate dependent, added on the device)
+//              + Qi_{i+1} + A1 Qi_i A1' [i>=1] + A2 Qi_{i-1} A2' [i>=2]         ; Y[T,T] = Qi_T (xf row)
+//   Y[i+1,i] = -A1 Qi_{i+1} + A2 Qi_i A1' [i>=1]   (i+1 <= T-1)                 ; Y[T,T-1] = Qi_T
+//   Y[i+2,i] = -A2 Qi_{i+1}                         (i+2 <= T-1)                 ; Y[T,T-2] = 0
+// with Qi_j = inv(2 Q_j), Q_T = Qf  (C rows: VAR_2/fast_mpc_eq_const.m:38-49,67-71; H: fast_mpc_objective.m:50-55).
+struct YTables {
+    std::vector<double> pool;
+    std::vector<int> ydi, y1i, y2i;
+};
+
+int intern_block(YTables &Y, const std::vector<double> &blk, size_t nn)
+{
+    bool zero = true;
+    for (double v : blk) if (v != 0.0) { zero = false; break; }
+    if (zero) return -1;
+    const size_t nblk = Y.pool.size() / nn;
+    for (size_t b = 0; b < nblk; ++b)
+        if (std::memcmp(Y.pool.data() + b * nn, blk.data(), nn * sizeof(double)) == 0) return (int)b;
+    Y.pool.insert(Y.pool.end(), blk.begin(), blk.end());
+    return (int)nblk;
+}
+
+void build_y_tables(const fmpc_sys *s, const std::vector<double> &qi, const std::vector<double> &qif, YTables &Y)
+{
+    const int n = s->n, T = s->T;
+    const size_t nn = (size_t)n * n;
+    const bool a2 = (s->var_order == 2);
+    auto A1 = [&](int r, int c) { return s->A1[(size_t)c * n + r]; };
+    auto A2 = [&](int r, int c) { return s->A2[(size_t)c * n + r]; };
+    auto Qi = [&](int j, int k) { return (j == T) ? qif[k] : qi[k]; };
+    Y.ydi.assign(T + 1, -1); Y.y1i.assign(T + 1, -1); Y.y2i.assign(T + 1, -1);
+    std::vector<double> blk(nn);
+    for (int i = 0; i <= T; ++i) {
+        // diagonal block
+        std::fill(blk.begin(), blk.end(), 0.0);
+        if (i == T) {
+            for (int k = 0; k < n; ++k) blk[(size_t)k * n + k] = Qi(T, k);
+        } else {
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c < n; ++c) {
+                    double v = (r == c) ? Qi(i + 1, r) : 0.0;
+                    if (i >= 1) for (int k = 0; k < n; ++k) v += A1(r, k) * Qi(i, k) * A1(c, k);
+                    if (i >= 2 && a2) for (int k = 0; k < n; ++k) v += A2(r, k) * Qi(i - 1, k) * A2(c, k);
+                    blk[(size_t)r * n + c] = v;
+                }
+        }
+        Y.ydi[i] = intern_block(Y, blk, nn);
+        // first sub-diagonal Y[i+1,i]
+        std::fill(blk.begin(), blk.end(), 0.0);
+        if (i + 1 <= T - 1) {
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c < n; ++c) {
+                    double v = -A1(r, c) * Qi(i + 1, c);
+                    if (i >= 1 && a2) for (int k = 0; k < n; ++k) v += A2(r, k) * Qi(i, k) * A1(c, k);
+                    blk[(size_t)r * n + c] = v;
+                }
+        } else if (i + 1 == T) {
+            for (int k = 0; k < n; ++k) blk[(size_t)k * n + k] = Qi(T, k);
+        }
+        Y.y1i[i] = intern_block(Y, blk, nn);
+        // second sub-diagonal Y[i+2,i]
+        std::fill(blk.begin(), blk.end(), 0.0);
+        if (i + 2 <= T - 1 && a2)
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c < n; ++c) blk[(size_t)r * n + c] = -A2(r, c) * Qi(i + 1, c);
+        Y.y2i[i] = intern_block(Y, blk, nn);
+    }
+    if (Y.pool.empty()) Y.pool.assign(nn, 0.0);
+}
+
+int validate_sys(const fmpc_sys *s)
+{
+    if (!s) return FMPC_ERR_NULL;
+    if (s->n < 1 || s->m < 1 || s->T < 1 || s->n > 512 || s->m > 4096 || s->T > 4096) return FMPC_ERR_DIM;
+    if (s->var_order != 1 && s->var_order != 2) return FMPC_ERR_DIM;
+    if (!s->Q || !s->Qf) return FMPC_ERR_Q_NOT_SQUARE;
+    if (!s->R) return FMPC_ERR_R_NOT_SQUARE;
+    if (!s->x_min || !s->x_max) return FMPC_ERR_X_BOUND_SIZE;
+    if (!s->u_min || !s->u_max) return FMPC_ERR_U_BOUND_SIZE;
+    if (!s->A1) return FMPC_ERR_NO_A;
+    if (s->var_order == 2 && !s->A2) return FMPC_ERR_NO_A;
+    if (!s->B) return FMPC_ERR_NO_B;
+    if (s->ramp_rows && (!s->du_min || !s->du_max)) return FMPC_ERR_U_BOUND_SIZE;
+    return FMPC_OK;
+}
+
+int validate_params(const fmpc_params *p)
+{
+    if (!p) return FMPC_ERR_NULL;
+    if (!(p->kappa > 0.0) || p->niters < 0 || p->ls_max < 0) return FMPC_ERR_PARAM;
+    if (!(p->beta > 0.0 && p->beta < 1.0) || !(p->alpha >= 0.0 && p->alpha < 1.0)) return FMPC_ERR_PARAM;
+    return FMPC_OK;
+}
+
+int ensure_device(int device)
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return FMPC_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FMPC_ERR_CUDA;
+    if (prop.major != 10) return FMPC_ERR_CUDA;       // built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return FMPC_ERR_CUDA;
+    return FMPC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+void fmpc_default_params(fmpc_params *p)
+{
+    if (!p) return;
+    p->kappa = 0.01;     // test_fast_mpc.m:53, README.md:551
+    p->niters = 5;       // test_fast_mpc.m:59
+    p->ls_max = 0;
+    p->alpha = 1e-4;     // inf_newton_solver.m:36
+    p->beta = 0.5;       // inf_newton_solver.m:37
+    p->tol_r = 1e-6;     // inf_newton_solver.m:9
+    p->tol_p = 1e-8;     // inf_newton_solver.m:19
+}
+
+int fmpc_device_count(void)
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+    int ok = 0;
+    for (int d = 0; d < cnt; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+const char *fmpc_strerror(int code)
+{
+    switch (code) {
+    case FMPC_OK: return "ok";
+    case FMPC_ERR_NULL: return "required pointer is NULL";
+    case FMPC_ERR_DIM: return "dimension out of range";
+    case FMPC_ERR_Q_NOT_SQUARE: return "State stage cost must a square matrix";
+    case FMPC_ERR_R_NOT_SQUARE: return "Control stage cost must a square matrix";
+    case FMPC_ERR_LIN_COST_SIZE: return "Linear state cost needs to be a vector of size n";
+    case FMPC_ERR_X_BOUND_SIZE: return "Check the state inequality constraints dimensions";
+    case FMPC_ERR_U_BOUND_SIZE: return "Check cotrol iequality constraint dimension";
+    case FMPC_ERR_NO_A: return "Define the state dynamics/equality constrained matrix";
+    case FMPC_ERR_NO_B: return "Define the control dynamics/equality constrained matrix";
+    case FMPC_ERR_A_SIZE: return "The equality state dynamics matrix size does not match";
+    case FMPC_ERR_B_SIZE: return "The equality control dynamics matrix size does not match";
+    case FMPC_ERR_INIT_SIZE: return "Initialization size mismatch (T*(n+m))";
+    case FMPC_ERR_NOT_PD: return "cost matrix is not positive definite";
+    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (dense Q/R or VAR_1 ramp rows; see DESIGN.md)";
+    case FMPC_ERR_BATCH: return "nbatch exceeds the handle's max_batch";
+    case FMPC_ERR_CUDA: return "no usable sm_100 CUDA device or CUDA runtime error (there is no CPU fallback)";
+    case FMPC_ERR_PARAM: return "invalid solver parameter";
+    default: return "unknown fmpc error";
+    }
+}
+
+void fmpc_destroy(fmpc_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void *p : h->sys_allocs) cudaFree(p);
+    DevBuf *bufs[] = {&h->ws, &h->counters, &h->d_x0, &h->d_x0pre, &h->d_uprev, &h->d_w, &h->d_xf, &h->d_X, &h->d_U,
+                      &h->d_nu0, &h->d_status, &h->d_iters, &h->d_a, &h->d_Uacc, &h->d_Xacc, &h->d_itacc};
+    for (DevBuf *b : bufs) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
+{
+    if (!out) return FMPC_ERR_NULL;
+    *out = nullptr;
+    int rc = validate_sys(s);
+    if (rc) return rc;
+    if (max_batch < 1) return FMPC_ERR_DIM;
+    const int n = s->n, m = s->m, T = s->T;
+    if (!is_diag(s->Q, n) || !is_diag(s->Qf, n) || !is_diag(s->R, m)) return FMPC_ERR_UNSUPPORTED;
+    if (s->ramp_rows) return FMPC_ERR_UNSUPPORTED;
+    for (int k = 0; k < n; ++k)
+        if (!(s->Q[(size_t)k * n + k] > 0.0) || !(s->Qf[(size_t)k * n + k] > 0.0)) return FMPC_ERR_NOT_PD;
+    for (int j = 0; j < m; ++j)
+        if (!(s->R[(size_t)j * m + j] > 0.0)) return FMPC_ERR_NOT_PD;
+    rc = ensure_device(device);
+    if (rc) return rc;
+
+    fmpc_handle *h = new (std::nothrow) fmpc_handle();
+    if (!h) return FMPC_ERR_CUDA;
+    h->device = device; h->n = n; h->m = m; h->T = T; h->var_order = s->var_order; h->max_batch = max_batch;
+    const bool a2 = (s->var_order == 2);
+
+    std::vector<double> B(s->B, s->B + (size_t)n * m), Bt((size_t)n * m);
+    for (int k = 0; k < n; ++k) for (int j = 0; j < m; ++j) Bt[(size_t)k * m + j] = B[(size_t)j * n + k];
+    std::vector<double> A1(s->A1, s->A1 + (size_t)n * n), A1t((size_t)n * n), A2((size_t)n * n, 0.0), A2t((size_t)n * n, 0.0);
+    if (a2) A2.assign(s->A2, s->A2 + (size_t)n * n);
+    for (int r = 0; r < n; ++r) for (int c = 0; c < n; ++c) { A1t[(size_t)r * n + c] = A1[(size_t)c * n + r]; A2t[(size_t)r * n + c] = A2[(size_t)c * n + r]; }
+    std::vector<double> r2(m), rl(m, 0.0), q2(n), q2f(n), qi(n), qif(n), ql(n, 0.0), qfl(n, 0.0);
+    for (int j = 0; j < m; ++j) { r2[j] = 2.0 * s->R[(size_t)j * m + j]; if (s->r) rl[j] = s->r[j]; }
+    for (int k = 0; k < n; ++k) {
+        q2[k] = 2.0 * s->Q[(size_t)k * n + k]; q2f[k] = 2.0 * s->Qf[(size_t)k * n + k];
+        qi[k] = 1.0 / q2[k]; qif[k] = 1.0 / q2f[k];
+        if (s->q) ql[k] = s->q[k];
+        if (s->qf) qfl[k] = s->qf[k];
+    }
+    YTables Y;
+    build_y_tables(s, qi, qif, Y);
+
+    DevSys &S = h->S;
+    S.n = n; S.m = m; S.T = T; S.has_a2 = a2 ? 1 : 0;
+    bool ok = true;
+#define UP(field, vec) do { S.field = upload(h, vec); if (!S.field) ok = false; } while (0)
+    UP(B, B); UP(Bt, Bt); UP(A1, A1); UP(A1t, A1t); UP(A2, A2); UP(A2t, A2t);
+    UP(r2, r2); UP(rl, rl); UP(q2, q2); UP(q2f, q2f); UP(qi, qi); UP(qif, qif); UP(ql, ql); UP(qfl, qfl);
+    std::vector<double> umin(s->u_min, s->u_min + m), umax(s->u_max, s->u_max + m), xmin(s->x_min, s->x_min + n), xmax(s->x_max, s->x_max + n);
+    UP(umin, umin); UP(umax, umax); UP(xmin, xmin); UP(xmax, xmax);
+    UP(ypool, Y.pool); UP(ydi, Y.ydi); UP(y1i, Y.y1i); UP(y2i, Y.y2i);
+#undef UP
+    if (ok && fmpc_solve_config(S, device, &h->cfg) != 0) ok = false;
+    if (ok) {
+        const WsLayout L = WsLayout::make(n, m, T);
+        h->ws_stride = L.total;
+        if (h->ws.ensure((size_t)h->cfg.grid * L.total * sizeof(double)) || h->counters.ensure(64)) ok = false;
+    }
+    if (ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    if (ok && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) ok = false;
+    if (!ok) { fmpc_destroy(h); return FMPC_ERR_CUDA; }
+    *out = h;
+    return FMPC_OK;
+}
+
+long long fmpc_workspace_bytes(const fmpc_handle *h) { return h ? (long long)h->ws.bytes : 0; }
+long long fmpc_launch_count(const fmpc_handle *h) { return h ? h->launches : 0; }
+
+long long fmpc_last_newton_iters(fmpc_handle *h)
+{
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    unsigned long long v = 0;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, h->counters.as<char>() + 8, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)v;
+}
+
+static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
+                       const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
+                       double *X, double *U, int *status, int *iters, cudaStream_t st)
+{
+    StepArgs A{};
+    A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
+    A.kappa = p->kappa; A.niters = p->niters; A.ls_max = p->ls_max;
+    A.alpha = p->alpha; A.beta = p->beta; A.tol_r = p->tol_r; A.tol_p = p->tol_p;
+    A.x0 = x0; A.x0_pre = x0_pre; A.w = w; A.xf = xf; A.X0 = X0; A.U0 = U0; A.nu0 = nu0;
+    A.X = X; A.U = U; A.status = status; A.iters = iters;
+    A.counter = h->counters.as<unsigned int>();
+    A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
+    A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
+    CU_OK(cudaMemsetAsync(h->counters.p, 0, 16, st));
+    fmpc_launch_solve(h->S, A, h->cfg, st);
+    CU_OK(cudaGetLastError());
+    h->launches += 1;
+    return FMPC_OK;
+}
+
+int fmpc_step_d(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
+                const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0,
+                const double *nu0, double *X, double *U, int *status, int *iters, void *stream)
+{
+    (void)u_prev;
+    if (!h || !x0 || !X || !U || !nu0) return FMPC_ERR_NULL;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nbatch < 0) return FMPC_ERR_DIM;
+    if (h->var_order == 2 && !x0_pre) return FMPC_ERR_A_SIZE;
+    if ((X0 == nullptr) != (U0 == nullptr)) return FMPC_ERR_INIT_SIZE;
+    if (nbatch == 0) return FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    return step_device(h, p, nbatch, x0, x0_pre, w, xf, X0, U0, nu0, X, U, status, iters,
+                       stream ? (cudaStream_t)stream : h->stream);
+}
+
+int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
+              const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0,
+              const double *nu0, double *X, double *U, int *status, int *iters, double *telapsed)
+{
+    (void)u_prev;
+    if (!h || !x0 || !X || !U) return FMPC_ERR_NULL;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nbatch < 0) return FMPC_ERR_DIM;
+    if (nbatch > h->max_batch) return FMPC_ERR_BATCH;
+    if (h->var_order == 2 && !x0_pre) return FMPC_ERR_A_SIZE;
+    if ((X0 == nullptr) != (U0 == nullptr)) return FMPC_ERR_INIT_SIZE;
+    if (telapsed) *telapsed = 0.0;
+    if (nbatch == 0) return FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    const int n = h->n, m = h->m, T = h->T;
+    const size_t nb = (size_t)nbatch, NBn = (size_t)(T + (xf ? 1 : 0)) * n;
+    cudaStream_t st = h->stream;
+    if (h->d_x0.ensure(nb * n * 8) || h->d_x0pre.ensure(nb * n * 8) || h->d_w.ensure(nb * T * n * 8) || h->d_xf.ensure(nb * n * 8) ||
+        h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
+        h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4))
+        return FMPC_ERR_CUDA;
+    const double *nu_src = nu0;
+    if (!nu0) {     // MATLAB default stream, one rand(length(b),1) per instance, instance after instance
+        h->h_nu.resize(nb * NBn);
+        for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
+        nu_src = h->h_nu.data();
+    }
+    CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, st));
+    if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, st));
+    if (w) CU_OK(cudaMemcpyAsync(h->d_w.p, w, nb * T * n * 8, cudaMemcpyHostToDevice, st));
+    if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.p, xf, nb * n * 8, cudaMemcpyHostToDevice, st));
+    if (X0) {
+        CU_OK(cudaMemcpyAsync(h->d_X.p, X0, nb * n * T * 8, cudaMemcpyHostToDevice, st));
+        CU_OK(cudaMemcpyAsync(h->d_U.p, U0, nb * m * T * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaEventRecord(h->ev0, st));
+    rc = step_device(h, p, nbatch, h->d_x0.as<double>(), x0_pre ? h->d_x0pre.as<double>() : nullptr,
+                     w ? h->d_w.as<double>() : nullptr, xf ? h->d_xf.as<double>() : nullptr,
+                     X0 ? h->d_X.as<double>() : nullptr, X0 ? h->d_U.as<double>() : nullptr, h->d_nu0.as<double>(),
+                     h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
+    if (rc) return rc;
+    CU_OK(cudaEventRecord(h->ev1, st));
+    CU_OK(cudaMemcpyAsync(X, h->d_X.p, nb * n * T * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaMemcpyAsync(U, h->d_U.p, nb * m * T * 8, cudaMemcpyDeviceToHost, st));
+    if (status) CU_OK(cudaMemcpyAsync(status, h->d_status.p, nb * 4, cudaMemcpyDeviceToHost, st));
+    if (iters) CU_OK(cudaMemcpyAsync(iters, h->d_iters.p, nb * 4, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(st));
+    if (telapsed) { float ms = 0.f; CU_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *telapsed = ms * 1e-3; }
+    return FMPC_OK;
+}
+
+int fmpc_step_z(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
+                const double *u_prev, const double *w, const double *xf, const double *z0, const double *nu0,
+                double *z, int *status, int *iters, double *telapsed)
+{
+    if (!h || !z) return FMPC_ERR_NULL;
+    if (nbatch < 0) return FMPC_ERR_DIM;
+    const int n = h->n, m = h->m, T = h->T;
+    const size_t nb = (size_t)nbatch;
+    std::vector<double> X(nb * n * T), U(nb * m * T), X0, U0;
+    if (z0) {       // de-interleave, README.md:558-570
+        X0.resize(nb * n * T); U0.resize(nb * m * T);
+        for (size_t b = 0; b < nb; ++b)
+            for (int t = 0; t < T; ++t) {
+                const double *zs = z0 + b * (size_t)T * (n + m) + (size_t)t * (n + m);
+                std::memcpy(&U0[b * m * T + (size_t)t * m], zs, m * 8);
+                std::memcpy(&X0[b * n * T + (size_t)t * n], zs + m, n * 8);
+            }
+    }
+    int rc = fmpc_step(h, p, nbatch, x0, x0_pre, u_prev, w, xf, z0 ? X0.data() : nullptr, z0 ? U0.data() : nullptr, nu0,
+                       X.data(), U.data(), status, iters, telapsed);
+    if (rc) return rc;
+    for (size_t b = 0; b < nb; ++b)
+        for (int t = 0; t < T; ++t) {
+            double *zs = z + b * (size_t)T * (n + m) + (size_t)t * (n + m);
+            std::memcpy(zs, &U[b * m * T + (size_t)t * m], m * 8);
+            std::memcpy(zs + m, &X[b * n * T + (size_t)t * n], n * 8);
+        }
+    return FMPC_OK;
+}
+
+int fmpc_frontend_nouter(const fmpc_handle *h, int mode)
+{
+    if (!h) return FMPC_ERR_NULL;
+    switch (mode) {
+    case FMPC_FE_FIXED_LOG: return 1;
+    case FMPC_FE_SOLVE_CHECK: return 5;                      // linspace(k_max,k_min,5), Fast_MPC2.m:89
+    case FMPC_FE_FIXED_NEWTON:
+    case FMPC_FE_SOLVE_FULL: {                               // k = 1; while k*length(z) >= 10e-3: k = k/10
+        const double N = (double)h->T * (h->n + h->m);
+        int cnt = 0;
+        double k = 1.0;
+        const double mu = 1.0 / 10;
+        while (k * N >= 10e-3) { ++cnt; k = mu * k; }
+        return cnt;
+    }
+    default: return FMPC_ERR_PARAM;
+    }
+}
+
+int fmpc_frontend(fmpc_handle *h, int mode, const fmpc_params *p, double k_min, double k_max, int nbatch,
+                  const double *x0, const double *x0_pre, const double *u_prev, const double *w, const double *xf,
+                  const double *X0, const double *U0, const double *nu0, double *X, double *U, int *status, int *iters,
+                  double *telapsed)
+{
+    if (!h || !p) return FMPC_ERR_NULL;
+    const int nouter = fmpc_frontend_nouter(h, mode);
+    if (nouter < 0) return nouter;
+    const size_t NBn = (size_t)(h->T + (xf ? 1 : 0)) * h->n;
+    fmpc_params q = *p;
+    if (mode == FMPC_FE_FIXED_LOG || mode == FMPC_FE_SOLVE_FULL || mode == FMPC_FE_SOLVE_CHECK) q.niters = 1000;   // nw = []
+    double k = (mode == FMPC_FE_FIXED_LOG) ? p->kappa : 1.0;
+    const double mu = 1.0 / 10;
+    double tsum = 0.0;
+    std::vector<int> it_acc;
+    if (iters) it_acc.assign((size_t)nbatch, 0);
+    const double *Xs = X0, *Us = U0;
+    for (int o = 0; o < nouter; ++o) {
+        if (mode == FMPC_FE_SOLVE_CHECK) k = k_max + (k_min - k_max) * (double)o / 4.0;   // linspace(k_max,k_min,5)
+        q.kappa = k;
+        double te = 0.0;
+        int rc = fmpc_step(h, &q, nbatch, x0, x0_pre, u_prev, w, xf, Xs, Us, nu0 ? nu0 + (size_t)o * NBn * nbatch : nullptr,
+                           X, U, status, iters, &te);
+        if (rc) return rc;
+        tsum += te;
+        if (iters) for (int b = 0; b < nbatch; ++b) it_acc[b] += iters[b];
+        Xs = X; Us = U;                                       // z = x_opt
+        if (mode == FMPC_FE_FIXED_NEWTON || mode == FMPC_FE_SOLVE_FULL) k = mu * k;
+    }
+    if (iters) for (int b = 0; b < nbatch; ++b) iters[b] = it_acc[b];
+    if (telapsed) *telapsed = tsum;
+    return FMPC_OK;
+}
+
+int fmpc_state_update_d(fmpc_handle *h, int nbatch, const double *x, const double *x_pre, const double *u, const double *w,
+                        double *x_next, void *stream)
+{
+    if (!h || !x || !u || !x_next) return FMPC_ERR_NULL;
+    if (h->var_order == 2 && !x_pre) return FMPC_ERR_A_SIZE;
+    if (nbatch <= 0) return nbatch < 0 ? FMPC_ERR_DIM : FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    fmpc_launch_state_update(h->S, nbatch, x, x_pre, u, w, x_next, stream ? stream : (void *)h->stream);
+    CU_OK(cudaGetLastError());
+    h->launches += 1;
+    return FMPC_OK;
+}
+
+int fmpc_state_update(fmpc_handle *h, int nbatch, const double *x, const double *x_pre, const double *u, const double *w,
+                      double *x_next)
+{
+    if (!h || !x || !u || !x_next) return FMPC_ERR_NULL;
+    if (h->var_order == 2 && !x_pre) return FMPC_ERR_A_SIZE;
+    if (nbatch <= 0) return nbatch < 0 ? FMPC_ERR_DIM : FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)nbatch, n = h->n, m = h->m;
+    // staging: x -> d_x0, x_pre -> d_x0pre, u -> d_uprev, w -> d_xf, out -> d_w
+    if (h->d_x0.ensure(nb * n * 8) || h->d_x0pre.ensure(nb * n * 8) || h->d_uprev.ensure(nb * m * 8) || h->d_xf.ensure(nb * n * 8) ||
+        h->d_w.ensure(nb * n * 8))
+        return FMPC_ERR_CUDA;
+    cudaStream_t st = h->stream;
+    CU_OK(cudaMemcpyAsync(h->d_x0.p, x, nb * n * 8, cudaMemcpyHostToDevice, st));
+    if (x_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x_pre, nb * n * 8, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(h->d_uprev.p, u, nb * m * 8, cudaMemcpyHostToDevice, st));
+    if (w) CU_OK(cudaMemcpyAsync(h->d_xf.p, w, nb * n * 8, cudaMemcpyHostToDevice, st));
+    int rc = fmpc_state_update_d(h, nbatch, h->d_x0.as<double>(), x_pre ? h->d_x0pre.as<double>() : nullptr, h->d_uprev.as<double>(),
+                                 w ? h->d_xf.as<double>() : nullptr, h->d_w.as<double>(), st);
+    if (rc) return rc;
+    CU_OK(cudaMemcpyAsync(x_next, h->d_w.p, nb * n * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(st));
+    return FMPC_OK;
+}
+
+int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, const double *a, const double *nu0,
+                     double *U_acc, double *X_acc, int *iters_acc, double *telapsed)
+{
+    if (!h || !a || !U_acc || !X_acc) return FMPC_ERR_NULL;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nbatch < 0 || K < 0) return FMPC_ERR_DIM;
+    if (nbatch > h->max_batch) return FMPC_ERR_BATCH;
+    if (telapsed) *telapsed = 0.0;
+    if (nbatch == 0 || K == 0) return FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    const size_t nb = (size_t)nbatch, n = h->n, m = h->m, T = h->T, NBn = T * n;
+    cudaStream_t st = h->stream;
+    if (h->d_x0.ensure(nb * n * 8) || h->d_x0pre.ensure(nb * n * 8) || h->d_uprev.ensure(nb * m * 8) ||
+        h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
+        h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4) || h->d_a.ensure(nb * n * K * 8) ||
+        h->d_Uacc.ensure(nb * m * K * 8) || h->d_Xacc.ensure(nb * n * K * 8) || h->d_itacc.ensure(nb * K * 4))
+        return FMPC_ERR_CUDA;
+    CU_OK(cudaMemcpyAsync(h->d_a.p, a, nb * n * K * 8, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemsetAsync(h->d_x0.p, 0, nb * n * 8, st));
+    CU_OK(cudaEventRecord(h->ev0, st));
+    for (int k = 0; k < K; ++k) {
+        const double *nu_src;
+        if (nu0) nu_src = nu0 + (size_t)k * nb * NBn;
+        else {
+            h->h_nu.resize(nb * NBn);
+            for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
+            nu_src = h->h_nu.data();
+            CU_OK(cudaStreamSynchronize(st));     // h_nu is reused next step
+        }
+        CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, st));
+        // x0 = a[:,k,b] + B u_prev ; x0_pre <- previous x0 ; warm start shifted one stage
+        fmpc_launch_shift_warm(h->S, nbatch, h->d_a.as<double>() + (size_t)k * n, (int)(n * K), h->d_X.as<double>(),
+                               h->d_U.as<double>(), h->d_x0.as<double>(), h->d_x0pre.as<double>(), h->d_uprev.as<double>(),
+                               k == 0, st);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+        rc = step_device(h, p, nbatch, h->d_x0.as<double>(), h->d_x0pre.as<double>(), nullptr, nullptr,
+                         k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(), h->d_nu0.as<double>(),
+                         h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
+        if (rc) return rc;
+        // logs: U_acc[:,k,b] = U(:,0,b), X_acc[:,k,b] = x0
+        CU_OK(cudaMemcpy2DAsync(h->d_Uacc.as<double>() + (size_t)k * m, m * K * 8, h->d_U.p, m * T * 8, m * 8, nb,
+                                cudaMemcpyDeviceToDevice, st));
+        CU_OK(cudaMemcpy2DAsync(h->d_Xacc.as<double>() + (size_t)k * n, n * K * 8, h->d_x0.p, n * 8, n * 8, nb,
+                                cudaMemcpyDeviceToDevice, st));
+        CU_OK(cudaMemcpy2DAsync(h->d_itacc.as<int>() + k, K * 4, h->d_iters.p, 4, 4, nb, cudaMemcpyDeviceToDevice, st));
+    }
+    CU_OK(cudaEventRecord(h->ev1, st));
+    CU_OK(cudaMemcpyAsync(U_acc, h->d_Uacc.p, nb * m * K * 8, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaMemcpyAsync(X_acc, h->d_Xacc.p, nb * n * K * 8, cudaMemcpyDeviceToHost, st));
+    if (iters_acc) CU_OK(cudaMemcpyAsync(iters_acc, h->d_itacc.p, nb * K * 4, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(st));
+    if (telapsed) { float ms = 0.f; CU_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *telapsed = ms * 1e-3; }
+    return FMPC_OK;
+}
+
+} // extern "C"

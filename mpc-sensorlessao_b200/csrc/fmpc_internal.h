@@ -1,0 +1,77 @@
+// Internal (non-ABI) declarations shared by the host layer and the CUDA kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+// Problem-constant device data of one handle.  All n x n "blocks" are ROW-major on the device
+// (the host layer transposes MATLAB's column-major input once, at fmpc_create).
+struct DevSys {
+    int n, m, T;
+    int has_a2;
+    const double *B;     // n x m, column-major:  B[k + n*j]      (rows k contiguous)
+    const double *Bt;    // m x n, column-major:  Bt[j + m*k] = B(k,j)
+    const double *A1;    // n x n, column-major:  A1[k + n*k']
+    const double *A1t;   // transpose
+    const double *A2, *A2t;
+    const double *r2;    // m : 2*R_jj
+    const double *rl;    // m : linear cost r
+    const double *q2;    // n : 2*Q_kk          (stages 1..T-1)
+    const double *q2f;   // n : 2*Qf_kk         (stage T)
+    const double *qi;    // n : 1/(2 Q_kk)
+    const double *qif;   // n : 1/(2 Qf_kk)
+    const double *ql;    // n : linear cost q
+    const double *qfl;   // n : linear cost qf
+    const double *umin, *umax, *xmin, *xmax;
+    // iterate-independent Schur blocks (row-major n x n each), de-duplicated pool + index tables (T+1 entries)
+    const double *ypool;
+    const int *ydi, *y1i, *y2i;   // block index per stage; -1 = zero block
+};
+
+struct StepArgs {
+    int nbatch, has_xf, cold;
+    double kappa;
+    int niters, ls_max;
+    double alpha, beta, tol_r, tol_p;
+    const double *x0, *x0_pre, *w, *xf, *X0, *U0, *nu0;
+    double *X, *U;
+    int *status, *iters;
+    unsigned int *counter;              // dynamic instance counter (zeroed before launch)
+    unsigned long long *iters_total;    // sum of Newton iterations (zeroed before launch)
+    double *ws;                         // per-CTA scratch
+    size_t ws_stride;                   // doubles per CTA
+};
+
+// Per-CTA scratch layout (in doubles), computed identically on host and device.
+struct WsLayout {
+    size_t nu, dnu, yv, rp, rpt, bv;            // (T+1) n each
+    size_t hx, hdx, dx, xt, rdx;                // T n each
+    size_t hu, hdu, du, ut, dbar, pinv, rdu;    // T m each
+    size_t Lf, L1, L2;                          // (T+1) n n each
+    size_t total;
+    __host__ __device__ static WsLayout make(int n, int m, int T)
+    {
+        WsLayout L;
+        size_t nb = (size_t)(T + 1) * n, tn = (size_t)T * n, tm = (size_t)T * m, bl = (size_t)(T + 1) * n * n;
+        size_t o = 0;
+        L.nu = o; o += nb; L.dnu = o; o += nb; L.yv = o; o += nb; L.rp = o; o += nb; L.rpt = o; o += nb; L.bv = o; o += nb;
+        L.hx = o; o += tn; L.hdx = o; o += tn; L.dx = o; o += tn; L.xt = o; o += tn; L.rdx = o; o += tn;
+        L.hu = o; o += tm; L.hdu = o; o += tm; L.du = o; o += tm; L.ut = o; o += tm; L.dbar = o; o += tm;
+        L.pinv = o; o += tm; L.rdu = o; o += tm;
+        L.Lf = o; o += bl; L.L1 = o; o += bl; L.L2 = o; o += bl;
+        L.total = (o + 15) & ~(size_t)15;
+        return L;
+    }
+};
+
+// status words (mirror include/fmpc.h)
+enum { ST_OK = 0, ST_EARLY_EXIT = 1, ST_NOT_PD = 2, ST_LS_MAX = 3, ST_NONFINITE = 4 };
+
+struct SolveLaunchCfg { int grid, block; size_t smem; };
+
+// kernels.cu
+int  fmpc_solve_config(const DevSys &S, int device, SolveLaunchCfg *cfg);        // 0 ok
+void fmpc_launch_solve(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
+void fmpc_launch_state_update(const DevSys &S, int nbatch, const double *x, const double *xpre, const double *u,
+                              const double *w, double *xnext, void *stream);
+void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int a_stride, double *X, double *U,
+                            double *x0, double *x0_pre, double *u_prev, int first, void *stream);

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def fref():
+    """The structured C oracle (built on demand into oracle/_ref/)."""
+    from oracle import fmpc_ref
+    fmpc_ref.build()
+    return fmpc_ref
+
+
+@pytest.fixture(scope="session")
+def pk():
+    import mpc_sensorlessao_b200 as pk
+    return pk

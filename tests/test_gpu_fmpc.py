@@ -1,0 +1,285 @@
+"""GPU parity tests of the fastMPC CUDA path, through the C-ABI (ctypes), against
+  * the structured C oracle on seeded inputs (sizes the oracle finishes in seconds),
+  * the committed golden fixtures (literal dense oracle),
+  * size-independent properties at BASELINE.json's full size (4096 instances, n=28, m=144, T=20).
+Tolerance (north-star): 1e-9 relative per array on U and X."""
+import numpy as np
+import pytest
+
+from cases import ref_solve, relerr, small_problem
+from test_golden_cpu import FMPC_FIXTURES, load_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def make_handle(pk, c, max_batch=None):
+    return pk.FastMPCBatch(c["A1"], c["A2"], c["B"], c["Q"], c["R"], c["Qf"], c["u_min"], c["u_max"], c["T"],
+                           c["x_min"], c["x_max"], max_batch=max_batch or c["nb"])
+
+
+def gpu_solve(pk, c, niters, kappa, hb=None, **kw):
+    own = hb is None
+    hb = hb or make_handle(pk, c)
+    out = hb.step(c["x0"], c["x0_pre"], c["w"], c["xf"], c["X0"], c["U0"], c["nu0"], kappa=kappa, niters=niters, **kw)
+    if own:
+        hb.close()
+    return out
+
+
+def assert_parity(out, ref, nb):
+    for b in range(nb):
+        assert relerr(out["U"][b], ref["U"][b]) < TOL, f"U instance {b}"
+        assert relerr(out["X"][b], ref["X"][b]) < TOL, f"X instance {b}"
+
+
+SMALL = [
+    dict(seed=1, n=6, m=4, T=5, nb=3, umax=2.0),
+    dict(seed=2, n=6, m=4, T=5, nb=3, umax=0.3, xf=True),
+    dict(seed=3, n=6, m=4, T=5, nb=3, umax=0.3, a2=False),
+    dict(seed=4, n=8, m=5, T=10, nb=5, umax=0.2, xf=True, warm=True),
+    dict(seed=5, n=8, m=5, T=10, nb=5, umax=0.1, warm=True),
+    dict(seed=6, n=5, m=7, T=1, nb=2, umax=0.5),                      # T = 1: single block row
+    dict(seed=7, n=5, m=7, T=2, nb=2, umax=0.5, xf=True),
+    dict(seed=8, n=33, m=20, T=6, nb=4, umax=0.5, warm=True),         # n > 32: multi-row-per-lane paths
+    dict(seed=9, n=1, m=1, T=3, nb=2, umax=1.0),                      # degenerate sizes
+    dict(seed=10, n=27, m=144, T=10, nb=4, umax=3.0, a2=False, warm=True),   # C1 shape, VAR(1)
+    dict(seed=11, n=28, m=144, T=20, nb=6, umax=0.5, warm=True),      # C2 shape, active barrier
+    dict(seed=12, n=66, m=144, T=30, nb=2, umax=1.0, warm=True),      # C5 shape
+]
+
+
+@pytest.mark.parametrize("kw", SMALL, ids=lambda k: f"s{k['seed']}_n{k['n']}m{k['m']}T{k['T']}")
+def test_parity_vs_structured_oracle(pk, fref, kw):
+    c = small_problem(**kw)
+    out = gpu_solve(pk, c, 6, 0.01)
+    ref = ref_solve(fref, c, 6, 0.01)
+    assert_parity(out, ref, c["nb"])
+    assert np.array_equal(out["iters"], ref["iters"])
+    assert np.array_equal(out["status"], ref["status"])
+
+
+@pytest.mark.parametrize("path", FMPC_FIXTURES, ids=lambda p: p.split("fmpc_")[-1][:-4])
+def test_parity_vs_golden(pk, path):
+    c = load_case(path)
+    out = gpu_solve(pk, c, c["niters"], c["kappa"])
+    assert_parity(out, c, c["nb"])
+    assert np.array_equal(out["iters"], c["iters"])
+    assert np.array_equal(out["status"] == 1, c["early_exit"])
+
+
+def test_line_search_both_regimes(pk, fref):
+    """Tight bounds: genuine halvings and the FP-saturated regime."""
+    for seed in (59, 61, 63, 67, 40, 41):
+        c = small_problem(seed, 6, 5, 6, 1, 0.05, warm=True)
+        c["U0"] = np.clip(c["U0"] * 10, -0.0499, 0.0499)
+        out = gpu_solve(pk, c, 4, 0.01)
+        ref = ref_solve(fref, c, 4, 0.01)
+        assert ref["halvings"][0] > 0
+        assert_parity(out, ref, 1)
+
+
+def test_ls_max_is_reported(pk):
+    c = small_problem(40, 6, 5, 6, 1, 0.05, warm=True)
+    c["U0"] = np.clip(c["U0"] * 10, -0.0499, 0.0499)
+    out = gpu_solve(pk, c, 2, 0.01, ls_max=5)
+    assert out["status"][0] == 3
+
+
+def test_not_pd_is_reported_per_instance_not_fatal(pk):
+    """Iterate outside the box far enough that a barrier weight goes hugely negative -> chol(Schur) fails
+    for that instance only (the reference would throw, inf_newton_solver.m:30)."""
+    c = small_problem(21, 6, 4, 5, 3, 0.5, warm=True)
+    out_ok = gpu_solve(pk, c, 3, 0.01)
+    c["U0"] = c["U0"].copy()
+    c["U0"][1] = np.nan
+    out = gpu_solve(pk, c, 3, 0.01)
+    assert out["status"][1] in (2, 4)
+    assert relerr(out["U"][0], out_ok["U"][0]) == 0.0 and relerr(out["U"][2], out_ok["U"][2]) == 0.0
+
+
+def test_empty_batch_and_batch_limit(pk):
+    c = small_problem(22, 4, 3, 3, 2, 1.0)
+    hb = make_handle(pk, c)
+    e = hb.step(np.zeros((0, 4)), np.zeros((0, 4)), None, None, None, None, np.zeros((0, 12)))
+    assert e["U"].shape == (0, 3, 3)
+    c3 = small_problem(22, 4, 3, 3, 3, 1.0)
+    with pytest.raises(pk.FmpcError) as ei:
+        gpu_solve(pk, c3, 2, 0.01, hb=hb)
+    assert ei.value.code == -15
+    hb.close()
+
+
+def test_matlab_stream_default_nu(pk, fref):
+    """nu0 = NULL draws rand(length(b),1) per instance from MT19937(5489), instance after instance."""
+    c = small_problem(23, 6, 4, 5, 3, 0.3, warm=True)
+    nu = np.random.RandomState(5489).random_sample(c["nu0"].size * 2).reshape(2, *c["nu0"].shape)
+    hb = make_handle(pk, c)
+    for call in range(2):
+        c["nu0"] = None
+        out = gpu_solve(pk, c, 1, 0.01, hb=hb)        # 1 step: z independent of nu, but iters/status are not
+        c["nu0"] = nu[call]
+        ref = ref_solve(fref, c, 1, 0.01)
+        assert_parity(out, ref, 3)
+    hb.close()
+    # a 2-step solve depends on nu through the accept/exit tests; same stream => same result
+    hb = make_handle(pk, c)
+    c["nu0"] = None
+    out = gpu_solve(pk, c, 4, 0.01, hb=hb)
+    c["nu0"] = nu[0]
+    assert_parity(out, ref_solve(fref, c, 4, 0.01), 3)
+    hb.close()
+
+
+def test_interleaved_entry_point_and_class_mirror(pk, fref):
+    """Fast_MPC2(...).mpc_fixed_log_newton(nw, k) -- the reference's own call shape (README.md:548-555)."""
+    from oracle import fastmpc_dense as fd
+    from mpc_sensorlessao_b200 import fast_mpc2
+    c = small_problem(24, 7, 5, 6, 1, 0.4, warm=False)
+    args = (c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"], c["u_max"],
+            -np.ones(5), np.ones(5), c["T"], c["x0"][0], c["x0_pre"][0], np.zeros(5), c["A1"], c["A2"], c["B"], c["w"][0],
+            None, None)
+    fast_mpc2.reset_matlab_stream()
+    z_gpu = pk.Fast_MPC2(*args).mpc_fixed_log_newton(5, 0.01)
+    z_gpu2 = pk.Fast_MPC2(*args).mpc_fixed_log_newton(5, 0.01)      # second object: next draws of the session stream
+    o = fd.Fast_MPC2(*args)
+    o.stream = fd.MatlabRand()
+    z_ref = o.mpc_fixed_log_newton(5, 0.01)
+    z_ref2 = o.mpc_fixed_log_newton(5, 0.01)
+    assert relerr(z_gpu, z_ref) < TOL and relerr(z_gpu2, z_ref2) < TOL
+    # warm start through x_init
+    z_w = pk.Fast_MPC2(*args[:-1], z_ref).mpc_fixed_log_newton(2, 0.01, nu0=np.full(c["T"] * 7, 0.5))
+    o2 = fd.Fast_MPC2(*args[:-1], z_ref)
+    assert relerr(z_w, o2.mpc_fixed_log_newton(2, 0.01, nu0=np.full(c["T"] * 7, 0.5))) < TOL
+
+
+def test_var1_class_mirror(pk):
+    from oracle import fastmpc_dense as fd
+    c = small_problem(25, 6, 4, 5, 1, 0.4, a2=False)
+    args = (c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"], c["u_max"],
+            -np.ones(4), np.ones(4), c["T"], c["x0"][0], np.zeros(4), c["A1"], c["B"], c["w"][0], None, None)
+    z = pk.Fast_MPC2_VAR1(*args).mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])
+    o = fd.Fast_MPC2_VAR1(*args, literal_bug=False)
+    o.inequality_const = lambda: fd.fast_mpc_ineq_const_var2(o)
+    assert relerr(z, o.mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])) < TOL
+
+
+def test_frontends_kappa_continuation(pk):
+    """mpc_fixed_newton / mpc_solve_full / mpc_solve_check / mpc_fixed_log (VAR_2/Fast_MPC2.m:88-144)."""
+    from oracle import fastmpc_dense as fd
+    c = small_problem(26, 6, 4, 5, 1, 0.6)
+    args = (c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"], c["u_max"],
+            -np.ones(4), np.ones(4), c["T"], c["x0"][0], c["x0_pre"][0], np.zeros(4), c["A1"], c["A2"], c["B"], c["w"][0],
+            None, None)
+    nouter = len(fd.Fast_MPC2.kappa_schedule(c["T"] * 10))
+    nus = np.random.RandomState(7).rand(max(nouter, 5), 30)
+    g, o = pk.Fast_MPC2(*args), fd.Fast_MPC2(*args)
+    assert relerr(g.mpc_fixed_newton(3, nu0=nus[:nouter]), o.mpc_fixed_newton(3, nu0_list=list(nus[:nouter]))) < TOL
+    assert relerr(g.mpc_solve_full(nu0=nus[:nouter]), o.mpc_solve_full(nu0_list=list(nus[:nouter]))) < 1e-7
+    assert relerr(g.mpc_solve_check(0.01, 1.0, nu0=nus[:5]), o.mpc_solve_check(0.01, 1.0, nu0_list=list(nus[:5]))) < 1e-7
+    assert relerr(g.mpc_fixed_log(0.01, nu0=nus[0]), o.mpc_fixed_log(0.01, nu0=nus[0])) < 1e-7
+
+
+def test_state_update(pk):
+    c = small_problem(27, 9, 6, 3, 17, 1.0)
+    hb = make_handle(pk, c)
+    rs = np.random.RandomState(0)
+    x, xp, u, w = rs.randn(17, 9), rs.randn(17, 9), rs.randn(17, 6), rs.randn(17, 9)
+    out = hb.state_update(x, xp, u, w)
+    ref = x @ c["A1"].T + xp @ c["A2"].T + u @ c["B"].T + w
+    assert relerr(out, ref) < 1e-13
+    assert relerr(hb.state_update(x, xp, u), ref - w) < 1e-13
+    hb.close()
+
+
+def test_closed_loop_matches_host_driven_loop(pk, fref):
+    """fmpc_closed_loop == the same loop driven from the host through the oracle."""
+    from mpc_sensorlessao_b200 import synth
+    p = synth.make_problem(3, 6, m1=4)            # n = 10, m = 16
+    nb, K = 3, 5
+    a = synth.aberrations(p, nb, K, seed=5)
+    nu = np.random.RandomState(1).rand(K, nb, p.T * p.n)
+    hb = pk.FastMPCBatch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, max_batch=nb)
+    out = hb.closed_loop(a, nu0=nu, niters=3)
+    hb.close()
+    u_prev = np.zeros((nb, p.m)); x0 = np.zeros((nb, p.n)); U = X = None
+    for k in range(K):
+        x0_pre = x0 if k else np.zeros((nb, p.n))
+        x0 = a[:, k] + u_prev @ p.B.T
+        c = dict(n=p.n, m=p.m, T=p.T, nb=nb, A1=p.A1, A2=p.A2, B=p.B, Q=p.Q, R=p.R, Qf=p.Qf, u_min=p.u_min, u_max=p.u_max,
+                 x_min=p.x_min, x_max=p.x_max, x0=x0, x0_pre=x0_pre, w=None, xf=None, nu0=nu[k],
+                 X0=None if k == 0 else np.concatenate([X[:, 1:], X[:, -1:]], axis=1),
+                 U0=None if k == 0 else np.concatenate([U[:, 1:], U[:, -1:]], axis=1))
+        ref = ref_solve(fref, c, 3, 0.01)
+        U, X = ref["U"], ref["X"]
+        u_prev = U[:, 0]
+        assert relerr(out["U_acc"][:, k], u_prev) < 1e-8, k
+        assert relerr(out["X_acc"][:, k], x0) < 1e-8, k
+        assert np.array_equal(out["iters"][:, k], ref["iters"])
+
+
+# ---- BASELINE.json full size: properties that need no oracle ---------------------------------
+@pytest.fixture(scope="module")
+def c2(pk):
+    from mpc_sensorlessao_b200 import synth
+    p = synth.make_problem(6, 20)
+    nb = 4096
+    wi = synth.warm_inputs(p, nb)
+    c = dict(n=p.n, m=p.m, T=p.T, nb=nb, A1=p.A1, A2=p.A2, B=p.B, Q=p.Q, R=p.R, Qf=p.Qf, u_min=p.u_min, u_max=p.u_max,
+             x_min=p.x_min, x_max=p.x_max, x0=wi["x0"], x0_pre=wi["x0_pre"], w=None, xf=None, nu0=wi["nu0"],
+             X0=wi["X0"], U0=wi["U0"])
+    hb = make_handle(pk, c)
+    out = gpu_solve(pk, c, 5, 0.01, hb=hb)
+    yield c, hb, out
+    hb.close()
+
+
+def test_c2_equality_constraints_hold(c2):
+    """r_p = 0 after a full Newton step: x_{i+1} = A1 x_i + A2 x_{i-1} + B u_i for every instance and stage."""
+    c, _, out = c2
+    X, U = out["X"], out["U"]
+    xs = np.concatenate([c["x0_pre"][:, None], c["x0"][:, None], X], axis=1)      # x_{-1}, x_0, x_1..x_T
+    pred = xs[:, 1:-1] @ c["A1"].T + xs[:, :-2] @ c["A2"].T + U @ c["B"].T
+    assert np.abs(pred - X).max() < 1e-9 * max(1.0, np.abs(X).max())
+    assert (np.abs(U) < 28.0).all() and np.isin(out["status"], (0, 1)).all() and (out["iters"] >= 1).all()
+
+
+def test_c2_sample_against_oracle(c2, fref):
+    c, _, out = c2
+    idx = np.random.RandomState(0).choice(c["nb"], 48, replace=False)
+    sub = dict(c)
+    for k in ("x0", "x0_pre", "nu0", "X0", "U0"):
+        sub[k] = c[k][idx]
+    sub["nb"] = len(idx)
+    ref = ref_solve(fref, sub, 5, 0.01)
+    for j, b in enumerate(idx):
+        assert relerr(out["U"][b], ref["U"][j]) < TOL and relerr(out["X"][b], ref["X"][j]) < TOL
+    assert np.array_equal(out["iters"][idx], ref["iters"])
+
+
+def test_c2_permutation_and_batch_size_invariance(pk, c2):
+    """An instance's result does not depend on its position in the batch or on the batch size (bit-exact)."""
+    c, hb, out = c2
+    perm = np.random.RandomState(1).permutation(c["nb"])
+    sub = dict(c)
+    for k in ("x0", "x0_pre", "nu0", "X0", "U0"):
+        sub[k] = c[k][perm]
+    out_p = gpu_solve(pk, sub, 5, 0.01, hb=hb)
+    assert np.array_equal(out_p["U"], out["U"][perm]) and np.array_equal(out_p["X"], out["X"][perm])
+    for k in ("x0", "x0_pre", "nu0", "X0", "U0"):
+        sub[k] = c[k][:7]
+    sub["nb"] = 7
+    out_s = gpu_solve(pk, sub, 5, 0.01, hb=hb)
+    assert np.array_equal(out_s["U"], out["U"][:7])
+
+
+def test_c2_full_step_is_independent_of_nu(pk, c2):
+    c, hb, _ = c2
+    sub = dict(c)
+    for k in ("x0", "x0_pre", "nu0", "X0", "U0"):
+        sub[k] = c[k][:64]
+    sub["nb"] = 64
+    a = gpu_solve(pk, sub, 1, 0.01, hb=hb)
+    sub["nu0"] = sub["nu0"][::-1].copy() * 3.0
+    b = gpu_solve(pk, sub, 1, 0.01, hb=hb)
+    assert relerr(a["U"], b["U"]) < 1e-11 and relerr(a["X"], b["X"]) < 1e-9

@@ -1,0 +1,68 @@
+"""GPU parity tests of the batched zernmodfit kernel (tolerance 1e-10 normwise, north-star)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import relerr
+from oracle import zernike_ref as zr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("N", [6, 10])
+def test_golden(pk, N):
+    g = np.load(os.path.join(GOLD, f"zernmodfit_N{N}.npz"))
+    zf = pk.ZernikeFitter(128, N, max_frames=16)
+    coef, _ = zf.fit(g["frames"].astype(np.float64))
+    assert relerr(coef, g["coef"]) < TOL
+    zf.close()
+
+
+@pytest.mark.parametrize("nL,N", [(128, 6), (64, 3), (33, 0), (16, 2)])
+def test_basis_mask_and_fit_vs_oracle(pk, nL, N):
+    zf = pk.ZernikeFitter(nL, N, max_frames=64)
+    r, th, is_in = zr.pupil_grid(nL)
+    n_, m_ = zr.mode_indices(N)
+    Z = zr.zernfun(n_, m_, r, th)
+    assert (zf.mask() == is_in).all() and zf.npix_in == r.shape[0] and zf.nmodes == n_.shape[0]
+    assert np.abs(zf.basis() - Z).max() < 1e-12
+    rs = np.random.RandomState(nL)
+    nf = 37                                         # ragged: not a multiple of the kernel's frame tile
+    frames = np.full((nf, nL * nL), np.nan)         # NaN outside the pupil must not leak (zernmodfit.m:30)
+    frames[:, is_in.T.reshape(-1)] = rs.randn(nf, Z.shape[0])
+    frames = frames.reshape(nf, nL, nL).transpose(0, 2, 1)
+    coef, _ = zf.fit(frames)
+    assert np.isfinite(coef).all()
+    assert relerr(coef, zr.fit_frames_literal(frames, N)) < TOL
+    zf.close()
+
+
+def test_known_coefficients_roundtrip_2000_frames(pk):
+    """BASELINE config 3 size: 2000 frames 128 x 128, N = 6; frames synthesised from known coefficients."""
+    zf = pk.ZernikeFitter(128, 6, max_frames=2000)
+    Z = zf.basis()
+    is_in = zf.mask()
+    rs = np.random.RandomState(3)
+    c = rs.randn(2000, 28)
+    frames = np.zeros((2000, 128 * 128))
+    frames[:, is_in.T.reshape(-1)] = c @ Z.T
+    frames = frames.reshape(2000, 128, 128).transpose(0, 2, 1)
+    coef, tel = zf.fit(frames)
+    assert relerr(coef, c) < TOL and tel > 0
+    # linearity
+    coef2, _ = zf.fit(2.5 * frames[:64] + frames[64:128])
+    assert relerr(coef2, 2.5 * c[:64] + c[64:128]) < TOL
+    zf.close()
+
+
+def test_function_mirror(pk):
+    r, th, is_in = zr.pupil_grid(64)
+    d = np.random.RandomState(0).randn(r.shape[0])
+    ad, nm = pk.zernmodfit(r, th, d, 4)
+    ad_ref, nm_ref = zr.zernmodfit(r, th, d, 4)
+    assert relerr(ad, ad_ref) < TOL and np.array_equal(nm, nm_ref)
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        pk.zernmodfit(r * 2, th, d, 4)

@@ -1,0 +1,77 @@
+"""CPU tests of the host-side mirror (argument checks with the reference's error strings,
+layout helpers, synthetic generators, import hygiene)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mk(pk, **kw):
+    n, m, T = 3, 2, 2
+    base = dict(Q=np.eye(n), R=np.eye(m), S=None, Qf=np.eye(n), q=None, r=None, qf=None, xmin=-np.ones(n),
+                xmax=np.ones(n), umin=-np.ones(m), umax=np.ones(m), dumin=None, dumax=None, T=T, x0=np.zeros(n),
+                x0_pre=np.zeros(n), u_prev=None, A1=np.eye(n), A2=np.eye(n), B=np.ones((n, m)), w=np.zeros(T * n),
+                xf=None, x_init=None)
+    base.update(kw)
+    return pk.Fast_MPC2(*base.values())
+
+
+@pytest.mark.parametrize("kw,exc,msg", [
+    (dict(x_init=np.zeros(3)), ValueError, "Initialization size mismatch"),
+    (dict(Q=np.ones((3, 4))), ValueError, "State stage cost must a square matrix"),
+    (dict(R=np.ones((2, 3))), ValueError, "Control stage cost must a square matrix"),
+    (dict(q=np.zeros(5)), ValueError, "Linear state cost"),
+    (dict(xmin=-np.ones(4)), ValueError, "state inequality constraints"),
+    (dict(umin=-np.ones(3)), ValueError, "Check cotrol iequality"),
+    (dict(A2=None), ValueError, "Define the state dynamics"),
+    (dict(B=None), ValueError, "Define the control dynamics"),
+    (dict(x0=np.zeros(4)), ValueError, "equality state dynamics matrix size"),
+    (dict(x0_pre=None), ValueError, "equality state dynamics matrix size"),
+    (dict(w=None), IndexError, "w"),
+])
+def test_mirror_raises_reference_errors_before_touching_the_gpu(pk, kw, exc, msg):
+    with pytest.raises(exc, match=msg):
+        _mk(pk, **kw).mpc_fixed_log_newton(1, 0.01)
+
+
+def test_interleave_roundtrip(pk):
+    T, n, m = 4, 3, 2
+    z = np.arange(T * (n + m), dtype=float)
+    U, X = pk.deinterleave(z, n, m, T)
+    assert U.shape == (T, m) and X.shape == (T, n)
+    assert np.array_equal(U[1], z[(n + m):(n + m) + m]) and np.array_equal(X[0], z[m:m + n])
+    assert np.array_equal(pk.interleave(U, X), z)
+
+
+def test_cold_start_midpoint(pk):
+    o = _mk(pk, umin=np.array([-1.0, 0.0]), umax=np.array([3.0, 2.0]), xmin=-2 * np.ones(3), xmax=4 * np.ones(3))
+    z = o.initialize().reshape(2, 5)
+    assert np.array_equal(z[:, :2], [[1, 1], [1, 1]]) and np.all(z[:, 2:] == 1.0)
+
+
+def test_synth_problem_is_stable_and_deterministic(pk):
+    from mpc_sensorlessao_b200 import synth
+    p = synth.make_problem(6, 20)
+    q = synth.make_problem(6, 20)
+    assert (p.n, p.m, p.T) == (28, 144, 20) and np.array_equal(p.A1, q.A1) and np.array_equal(p.B, q.B)
+    comp = np.block([[p.A1, p.A2], [np.eye(28), np.zeros((28, 28))]])
+    assert np.abs(np.linalg.eigvals(comp)).max() < 1.0
+    p27 = synth.make_problem(6, 10, var_order=1, drop_piston=True)
+    assert (p27.n, p27.A2) == (27, None)
+    assert synth.make_problem(10, 30).n == 66
+    a = synth.aberrations(p, 3, 7)
+    assert a.shape == (3, 7, 28) and np.isfinite(a).all()
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    pkg = os.path.join(ROOT, "mpc-sensorlessao_b200")
+    for dp_, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".c", ".m")):
+                src = open(os.path.join(dp_, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "fmpc_ref" not in src and "fref_" not in src, f
