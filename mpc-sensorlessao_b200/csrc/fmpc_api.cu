@@ -327,8 +327,24 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     std::vector<double> umin(s->u_min, s->u_min + m), umax(s->u_max, s->u_max + m), xmin(s->x_min, s->x_min + n), xmax(s->x_max, s->x_max + n);
     UP(umin, umin); UP(umax, umax); UP(xmin, xmin); UP(xmax, xmax);
     UP(ypool, Y.pool); UP(ydi, Y.ydi); UP(y1i, Y.y1i); UP(y2i, Y.y2i);
+    {   // pair-product matrix for the DMMA path
+        const int np = n * (n + 1) / 2, Mp = (np + 7) & ~7, mp = (m + 3) & ~3;
+        std::vector<double> G((size_t)Mp * mp, 0.0);
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) {
+                double *row = &G[(size_t)(r * (r + 1) / 2 + c) * mp];
+                for (int j = 0; j < m; ++j) row[j] = B[(size_t)j * n + r] * B[(size_t)j * n + c];
+            }
+        S.npairs = np; S.Mp = Mp; S.mp = mp;
+        UP(G, G);
+    }
 #undef UP
-    if (ok && fmpc_solve_config(S, device, &h->cfg) != 0) ok = false;
+    if (ok) {
+        const char *force_v1 = getenv("FMPC_FORCE_V1");
+        if ((force_v1 && force_v1[0] == '1') || fmpc_mma_config(S, device, &h->cfg) != 0) {
+            if (fmpc_solve_config(S, device, &h->cfg) != 0) ok = false;
+        }
+    }
     if (ok) {
         const WsLayout L = WsLayout::make(n, m, T);
         h->ws_stride = L.total;
@@ -368,7 +384,8 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     CU_OK(cudaMemsetAsync(h->counters.p, 0, 16, st));
-    fmpc_launch_solve(h->S, A, h->cfg, st);
+    if (h->cfg.use_mma) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
+    else fmpc_launch_solve(h->S, A, h->cfg, st);
     CU_OK(cudaGetLastError());
     h->launches += 1;
     return FMPC_OK;

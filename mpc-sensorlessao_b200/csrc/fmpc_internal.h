@@ -25,6 +25,10 @@ struct DevSys {
     // iterate-independent Schur blocks (row-major n x n each), de-duplicated pool + index tables (T+1 entries)
     const double *ypool;
     const int *ydi, *y1i, *y2i;   // block index per stage; -1 = zero block
+    // DMMA path: pair-product matrix G[p][j] = B(r,j) B(c,j), p = r(r+1)/2 + c (r >= c), row-major Mp x mp,
+    // so that  B diag(w_t) B'  for ALL stages is one GEMM  G (Mp x mp) * W (mp x T)
+    const double *G;
+    int npairs, Mp, mp;
 };
 
 struct StepArgs {
@@ -47,6 +51,7 @@ struct WsLayout {
     size_t hx, hdx, dx, xt, rdx;                // T n each
     size_t hu, hdu, du, ut, dbar, pinv, rdu;    // T m each
     size_t Lf, L1, L2;                          // (T+1) n n each
+    size_t Dsc;                                 // T * Mp : packed lower triangles of B diag(w_t) B'
     size_t total;
     __host__ __device__ static WsLayout make(int n, int m, int T)
     {
@@ -58,6 +63,7 @@ struct WsLayout {
         L.hu = o; o += tm; L.hdu = o; o += tm; L.du = o; o += tm; L.ut = o; o += tm; L.dbar = o; o += tm;
         L.pinv = o; o += tm; L.rdu = o; o += tm;
         L.Lf = o; o += bl; L.L1 = o; o += bl; L.L2 = o; o += bl;
+        { size_t np = (size_t)n * (n + 1) / 2, Mp = (np + 7) & ~(size_t)7; L.Dsc = o; o += (size_t)T * Mp; }
         L.total = (o + 15) & ~(size_t)15;
         return L;
     }
@@ -66,7 +72,7 @@ struct WsLayout {
 // status words (mirror include/fmpc.h)
 enum { ST_OK = 0, ST_EARLY_EXIT = 1, ST_NOT_PD = 2, ST_LS_MAX = 3, ST_NONFINITE = 4 };
 
-struct SolveLaunchCfg { int grid, block; size_t smem; };
+struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; };
 
 // kernels.cu
 int  fmpc_solve_config(const DevSys &S, int device, SolveLaunchCfg *cfg);        // 0 ok
@@ -75,3 +81,7 @@ void fmpc_launch_state_update(const DevSys &S, int nbatch, const double *x, cons
                               const double *w, double *xnext, void *stream);
 void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int a_stride, double *X, double *U,
                             double *x0, double *x0_pre, double *u_prev, int first, void *stream);
+
+// kernel_mma.cu : DMMA path (n <= 32)
+int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable
+void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
