@@ -337,6 +337,12 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
             }
         S.npairs = np; S.Mp = Mp; S.mp = mp;
         UP(G, G);
+        const size_t nblk = Y.pool.size() / ((size_t)n * n);
+        std::vector<double> ypk(nblk * Mp, 0.0);
+        for (size_t bidx = 0; bidx < nblk; ++bidx)
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c <= r; ++c) ypk[bidx * Mp + r * (r + 1) / 2 + c] = Y.pool[bidx * n * n + (size_t)r * n + c];
+        UP(ypk, ypk);
     }
 #undef UP
     if (ok) {

@@ -29,6 +29,7 @@ struct DevSys {
     // so that  B diag(w_t) B'  for ALL stages is one GEMM  G (Mp x mp) * W (mp x T)
     const double *G;
     int npairs, Mp, mp;
+    const double *ypk;   // the pool blocks again, lower triangles packed by pair index: [block][Mp]
 };
 
 struct StepArgs {

@@ -1,19 +1,22 @@
 // fastMPC batched Newton solve -- DMMA path for n <= 32 (sm_100a, fp64).
 //
-// Same algorithm and the same per-instance control flow as the generic kernel in fmpc_kernels.cu
-// (one persistent CTA per MPC instance; inf_newton_solver.m:10-41 on the block structure), but every
-// dense contraction runs on the FP64 tensor pipe (mma.sync.aligned.m8n8k4.f64 = DMMA, measured
-// 37.2 TFLOP/s on B200 = the FP64 roofline):
-//   * B diag(w_t) B' for ALL stages at once as ONE GEMM  G (npairs x m) * W (m x T), G[p][j] = B(r,j) B(c,j)
-//     precomputed on the host: no 28 -> 32 padding waste, symmetric half only;
-//   * band-2 block Cholesky of the Schur complement: syrk / gemm updates as 8 x 8 x 4 DMMA tiles on
-//     shared-memory blocks (row-major, leading dimension = 4 mod 8 doubles: conflict-free fragment loads);
-//   * the diagonal block is factored by ONE warp with rows in registers (right-looking, column broadcast
-//     through a 32-double shared vector), then inverted explicitly (column per lane), so that both
-//     triangular solves with n right-hand sides become DMMA products with inv(L)' and the forward /
-//     backward substitutions become GEMVs.
+// Same algorithm and per-instance control flow as the generic kernel in fmpc_kernels.cu (one persistent
+// CTA per MPC instance; inf_newton_solver.m:10-41 on the block structure), but every dense contraction
+// runs on the FP64 tensor pipe (mma.sync.aligned.m8n8k4.f64 = DMMA, measured 37.2 TFLOP/s on B200 = the
+// FP64 roofline) with operands staged in shared memory (row-major, leading dimension = 4 mod 8 doubles:
+// conflict-free fragment loads):
+//   * every application of C / C' (r_p = Cz - b, C inv(Phi) r_d, C' dnu, trial residuals) is a set of GEMMs
+//     over the horizon:  B U, A1 X, A2 X (n x T) and B' N, A1' N, A2' N (m x T, n x T); the elementwise
+//     work (barrier terms, inv(Phi) scaling, trial point) is fused into the staging / epilogues;
+//   * B diag(w_t) B' for ALL stages as ONE GEMM  G (npairs x m) * W (m x T),  G[p][j] = B(r,j) B(c,j)
+//     precomputed on the host: symmetric half only, no 28 -> 32 padding;
+//   * band-2 block Cholesky of the Schur complement: syrk / gemm updates as 8 x 8 x 4 tiles on five
+//     shared-memory blocks; the diagonal block is factored by ONE warp with rows in registers
+//     (S = U D U', pivot chain through shuffles) and inverted explicitly, so both triangular solves with
+//     n right-hand sides become DMMA products with inv(L)' and the substitutions become GEMVs.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "fmpc_internal.h"
 #include "fmpc_device.cuh"
 
@@ -23,7 +26,8 @@ namespace {
 
 constexpr int NTHREADS = 128;
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int TCHUNK = 24;          // stages per pass of the G * W GEMM (3 DMMA column tiles)
+constexpr int MAXTT = 3;             // horizon (column) tiles accumulated together by one warp
+constexpr int CTAS_PER_SM = 5;
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b)
 {
@@ -32,139 +36,312 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, con
 }
 
 struct Geom {
-    int n, KP, ld, RP, nt, ks, lds, mp, ldp;
-    __host__ __device__ static Geom make(int n, int m)
+    int n, KP, ld, RP, nt, ks, lds, ldu, mp, ldp, TP, ntt;
+    __host__ __device__ static int kp_of(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 28 ? 28 : 32)); }
+    __host__ __device__ static Geom make(int n, int m, int T)
     {
         Geom g;
         g.n = n;
-        g.KP = (n + 3) & ~3;
+        g.KP = kp_of(n);                                  // compile-time sizes of the kernel instantiations
         g.ld = (g.KP % 8 == 4) ? g.KP : g.KP + 4;
-        g.RP = (n + 7) & ~7;
+        g.RP = (g.KP + 7) & ~7;
         g.nt = g.RP / 8;
         g.ks = g.KP / 4;
-        g.lds = g.RP + 1;
+        g.lds = g.KP + 1;                                 // S scratch (odd: row-per-lane loads are conflict-free)
+        g.ldu = g.KP + 2;                                 // U scratch (16 B aligned rows, conflict-free 128-bit row stores)
         g.mp = (m + 3) & ~3;
         g.ldp = (g.mp % 8 == 4) ? g.mp : g.mp + 4;
+        g.TP = (T + 7) & ~7;
+        g.ntt = g.TP / 8;
         return g;
     }
     __host__ __device__ size_t blk() const { return (size_t)RP * ld; }
-    // doubles of dynamic shared memory
-    __host__ __device__ size_t smem_doubles() const
+    __host__ __device__ size_t ops_doubles() const
     {
-        size_t ops = 6 * blk();
-        const size_t pch = (size_t)TCHUNK * ldp;
-        if (pch > ops) ops = pch;
-        return ops + (size_t)RP * lds + 32 * 3 + 64 + 32 + 34;
+        size_t a = 5 * blk();
+        const size_t b = (size_t)TP * ldp + (size_t)(TP + 2) * ld;   // staging: U-like operand + X-like operand
+        if (b > a) a = b;
+        return (a + 1) & ~(size_t)1;
     }
+    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + 32 * 3 + 64 + 32 + 36; }
 };
 
-// C(8x8 tile) += A(rows ra.., k) * B(rows rb.., k)'   over ksteps k-steps of 4, operands in shared memory
+// C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory
 __device__ __forceinline__ void tile_nt(double &c0, double &c1, const double *A, const double *Bm, int ksteps)
 {
 #pragma unroll 4
     for (int k = 0; k < ksteps; ++k) dmma(c0, c1, A[4 * k], Bm[4 * k]);
 }
 
-// ---------------------------------------------------------------------------------------------
-// One warp: in-register Cholesky of the n x n block in bS (lower triangle, leading dimension lds),
-// then explicit inverse of the factor.  Outputs: bLinv (RP x ld, zero padded, operand layout) and
-// gLinv (n x n row-major, global scratch for the backward pass).  Returns 0 or failing column + 1.
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ int warp_potrf_inverse(double *bS, int lds, double *bLinv, int ld, int KP, double *gLinv, int n,
-                                               double *colbuf, double *rsv, int lane)
+// acc[tt] += A(row arow of a GLOBAL row-major matrix) * Bs(shared rows 8 tt + .., ldb)'
+//   Ag : points at A(arow, q);  Bs : points at Bs(row of tile 0, q);  entries with column >= Kv read as 0
+__device__ __forceinline__ void mma_gA_sB(double (&acc)[MAXTT][2], const double *Ag, bool arow_ok, int Kv, int ksteps,
+                                          const double *Bs, int ldb, int ntt_live, int q)
 {
-    double a[32];
-    const int r = lane;
+    for (int k0 = 0; k0 < ksteps; k0 += 12) {
+        double af[12];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) a[c] = (r < n && c <= r) ? bS[r * lds + c] : ((c == r) ? 1.0 : 0.0);
-    int info = 0;
+        for (int kk = 0; kk < 12; ++kk) {
+            const int kc = 4 * (k0 + kk) + q;
+            af[kk] = (k0 + kk < ksteps && arow_ok && kc < Kv) ? __ldg(Ag + 4 * (k0 + kk)) : 0.0;
+        }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        if (k < n) {
-            double *cb = colbuf + (k & 1) * 32;
-            cb[lane] = a[k];                               // unscaled column k (valid for lanes >= k)
-            __syncwarp();
-            const double d = cb[k];
-            if (!(d > 0.0) || !isfinite(d)) { if (!info) info = k + 1; }
-            const double dinv = 1.0 / d;
-            const double rs = rsqrt(d);
-            const double t = a[k] * dinv;
+        for (int kk = 0; kk < 12; ++kk) {
+            if (k0 + kk < ksteps) {
 #pragma unroll
-            for (int c = k + 1; c < 32; ++c)
-                if (c < n) a[c] = fma(-t, cb[c], a[c]);   // rank-1 update; entries above the diagonal are never read
-            a[k] *= rs;                                    // L(r,k)
-            if (lane == 0) rsv[k] = rs;                    // 1 / L(k,k)
+                for (int tt = 0; tt < MAXTT; ++tt)
+                    if (tt < ntt_live) dmma(acc[tt][0], acc[tt][1], af[kk], Bs[(size_t)(8 * tt) * ldb + 4 * (k0 + kk)]);
+            }
         }
     }
-    if (info) return info;
-    // L rows -> bS (row r by lane r; lds odd: conflict-free), then inverse column j by lane j
+}
+
+// 1/x for a positive normal x: MUFU.RCP64H seed + two Newton steps (<= 1 ulp), no slow path.
+__device__ __forceinline__ double rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp: Cholesky of the n x n block in bS (lower triangle, leading dimension NP+1) and explicit
+// inverse of the factor, NP = padded size (compile time; rows/cols n..NP-1 behave as identity).
+//   S = U D U'  (U unit lower, D = diag(d_k)) right-looking with row r in the registers of lane r; the
+//   pivot chain runs through shuffles and each lane updates its own diagonal entry, so the serial work
+//   per column is shfl -> rcp -> 2 FMAs; the rank-1 update reads the column from a 32-double shared
+//   vector (128-bit broadcast loads).  Then V = inv(U) column j by lane j and
+//   inv(L) = diag(1/sqrt(d)) V  with ONE rsqrt per lane.
+// bS is consumed before bLinv is written (they may alias); bU must not alias either.
+// Outputs: bLinv (RP x ld operand block, zero padded) and gLinv (n x n row-major, global scratch).
+// Returns 0 or failing column + 1.
+// ---------------------------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ int warp_potrf_inverse(const double *bS, double *bU, double *bLinv, int ld, double *gLinv, int n,
+                                                  double *colbuf, double *rsv, int lane)
+{
+    constexpr int LDS_ = NP + 1, LDU = NP + 2, RP_ = (NP + 7) & ~7;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r = lane;
+    double a[NP];
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-        if (c < n && r < n && c <= r) bS[r * lds + c] = a[c];
-    __syncwarp();
-    double x[32];
-    const int j = lane;
+    for (int c = 0; c < NP; ++c) a[c] = (r < n && c < r) ? bS[r * LDS_ + c] : 0.0;
+    double diag = (r < n) ? bS[r * LDS_ + r] : 1.0;
+    double dpiv = 1.0;
+    int info = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        x[i] = 0.0;
-        if (i < n) {
-            double s0 = 0.0, s1 = 0.0;
+    for (int k = 0; k < NP; ++k) {
+        const double d = __shfl_sync(FULL, diag, k);        // pivot of column k (lane k's diagonal entry)
+        if (!(d > 0.0) || !(d < 1.0e300)) { if (!info) info = k + 1; }
+        if (lane == k) dpiv = d;
+        const double at = a[k];                             // unscaled column entry
+        if (k + 1 < NP) {
+            double *cb = colbuf + (k & 1) * 32;
+            cb[lane] = at;
+            const double dinv = rcp_pos(d);
+            const double t = at * dinv;                     // U(r,k)
+            a[k] = t;
+            diag = fma(-t, at, diag);                       // own diagonal entry (only lanes > k use it)
+            __syncwarp();
+            if ((k + 1) & 1) a[k + 1] = fma(-t, cb[k + 1], a[k + 1]);
 #pragma unroll
-            for (int k = 0; k + 1 < i; k += 2) {
-                s0 = fma(bS[i * lds + k], x[k], s0);
-                s1 = fma(bS[i * lds + k + 1], x[k + 1], s1);
+            for (int c2 = (k + 2) & ~1; c2 + 1 < NP; c2 += 2) {
+                const double2 p = *reinterpret_cast<const double2 *>(cb + c2);
+                a[c2] = fma(-t, p.x, a[c2]);
+                a[c2 + 1] = fma(-t, p.y, a[c2 + 1]);
             }
-            if (i & 1) s0 = fma(bS[i * lds + i - 1], x[i - 1], s0);
-            const double rs = rsv[i];
-            x[i] = (i < j) ? 0.0 : ((i == j) ? rs : -(s0 + s1) * rs);
         }
+    }
+    if (info) return info;                                  // uniform: d is the same in every lane
+    rsv[lane] = rsqrt(dpiv);
+#pragma unroll
+    for (int c = 0; c + 1 < NP; c += 2)
+        if (r < NP) *reinterpret_cast<double2 *>(bU + r * LDU + c) = make_double2(a[c], a[c + 1]);
+    __syncwarp();
+    // V = inv(U): column j by lane j;  v[i] = -(sum_{k<i} U(i,k) v[k]) for i > j, v[j] = 1, v[i<j] = 0
+    const int j = lane;
+    double v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+            const double2 p = *reinterpret_cast<const double2 *>(bU + i * LDU + k);
+            s0 = fma(p.x, v[k], s0);
+            s1 = fma(p.y, v[k + 1], s1);
+        }
+        if (i & 1) s0 = fma(bU[i * LDU + i - 1], v[i - 1], s0);
+        v[i] = (i < j) ? 0.0 : ((i == j) ? 1.0 : -(s0 + s1));
     }
     const bool live = (j < n);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (i < n) {
-            const double v = live ? x[i] : 0.0;
-            if (j < KP) bLinv[i * ld + j] = v;
-            if (live) gLinv[i * n + j] = v;
-        }
+    for (int i = 0; i < RP_; ++i) {
+        double val = 0.0;
+        if (i < NP) val = (live && i < n) ? v[i < NP ? i : 0] * rsv[i] : 0.0;    // inv(L)(i,j) = v(i,j) / sqrt(d_i)
+        if (j < NP) bLinv[i * ld + j] = val;
+        if (live && i < n) gLinv[i * n + j] = val;
     }
     return 0;
+}
+
+// Everything a phase needs; lives in registers / constant bank.
+struct KC {
+    const DevSys &S;
+    int n, m, T, NB, has_xf;
+    int tid, lane, wid, gq, q;
+    int ld, nt, ks, mp, ldp, TP, ntt;
+    double *Us, *Xs, *red;
+};
+
+// ---- out = sgn * (C v - sub)  for v staged as  Us [TP][ldp] (u-like rows t)  and  Xs [(TP+2)][ld]
+//      (row rr <-> x-like source row rr - 2; source row j-1 holds x_j).  Rows follow
+//      VAR_2/fast_mpc_eq_const.m:38-49,67-71.  out / sub : NB*n global vectors.
+__device__ __noinline__ void mma_apply_C(const KC &k, const double *sub, double *out, bool negate)
+{
+    const DevSys &S = k.S;
+    const int n = k.n, m = k.m, T = k.T;
+    for (int mt = k.wid; mt < k.nt; mt += NWARPS) {
+        const int row = 8 * mt + k.gq;
+        const bool rok = row < n;
+        for (int tt0 = 0; tt0 < k.ntt; tt0 += MAXTT) {
+            const int live = min(MAXTT, k.ntt - tt0);
+            double acc[MAXTT][2];
+#pragma unroll
+            for (int tt = 0; tt < MAXTT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+            // B u_i
+            mma_gA_sB(acc, S.Bt + (size_t)row * m + k.q, rok, m, k.mp / 4, k.Us + (size_t)(8 * tt0 + k.gq) * k.ldp + k.q, k.ldp, live, k.q);
+            // A1 x_i  (x_i = source row i-1 = staged row i+1)
+            mma_gA_sB(acc, S.A1t + (size_t)row * n + k.q, rok, n, k.ks, k.Xs + (size_t)(8 * tt0 + k.gq + 1) * k.ld + k.q, k.ld, live, k.q);
+            // A2 x_{i-1}  (source row i-2 = staged row i)
+            if (S.has_a2)
+                mma_gA_sB(acc, S.A2t + (size_t)row * n + k.q, rok, n, k.ks, k.Xs + (size_t)(8 * tt0 + k.gq) * k.ld + k.q, k.ld, live, k.q);
+#pragma unroll
+            for (int tt = 0; tt < MAXTT; ++tt) {
+                if (tt < live) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int i = 8 * (tt0 + tt) + 2 * k.q + e;
+                        if (rok && i < T) {
+                            const double v = k.Xs[(size_t)(i + 2) * k.ld + row] - acc[tt][e] - sub[(size_t)i * n + row];
+                            out[(size_t)i * n + row] = negate ? -v : v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (k.has_xf)
+        for (int r = k.tid; r < n; r += NTHREADS) {
+            const double v = k.Xs[(size_t)(T - 1 + 2) * k.ld + r] - sub[(size_t)T * n + r];
+            out[(size_t)T * n + r] = negate ? -v : v;
+        }
+}
+
+// ---- C' v for v staged as Ns = Xs region [(TP+2)][ld], row rr <-> v_rr for rr < T, rows >= T zero.
+//      MODE 0 (init):  hu = B' nu_t ,  hx = (C' nu)_x                                  (stored)
+//      MODE 1 (step):  hdu, hdx stored and  du = -(rdu - hdu) w ,  dx = -(rdx + hdx) qi     (inf_newton_solver.m:34-35)
+template <int MODE>
+__device__ __noinline__ void mma_apply_Ct(const KC &k, const double *vglob, double *hu, double *hx, const double *rdu,
+                                          const double *rdx, const double *w, double *du, double *dx)
+{
+    const DevSys &S = k.S;
+    const int n = k.n, m = k.m, T = k.T;
+    const int mtu = (m + 7) / 8;
+    for (int task = k.wid; task < mtu + k.nt; task += NWARPS) {
+        const bool upart = task < mtu;
+        const int mt = upart ? task : task - mtu;
+        const int row = 8 * mt + k.gq;
+        const bool rok = row < (upart ? m : n);
+        for (int tt0 = 0; tt0 < k.ntt; tt0 += MAXTT) {
+            const int live = min(MAXTT, k.ntt - tt0);
+            double acc[MAXTT][2];
+#pragma unroll
+            for (int tt = 0; tt < MAXTT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+            if (upart) {
+                // (B' v_t)(j) : A = B' as row-major [j][k] = column-major B
+                mma_gA_sB(acc, S.B + (size_t)row * n + k.q, rok, n, k.ks, k.Xs + (size_t)(8 * tt0 + k.gq) * k.ld + k.q, k.ld, live, k.q);
+            } else {
+                // A1' v_{t+1} + A2' v_{t+2}
+                mma_gA_sB(acc, S.A1 + (size_t)row * n + k.q, rok, n, k.ks, k.Xs + (size_t)(8 * tt0 + k.gq + 1) * k.ld + k.q, k.ld, live, k.q);
+                if (S.has_a2)
+                    mma_gA_sB(acc, S.A2 + (size_t)row * n + k.q, rok, n, k.ks, k.Xs + (size_t)(8 * tt0 + k.gq + 2) * k.ld + k.q, k.ld, live, k.q);
+            }
+#pragma unroll
+            for (int tt = 0; tt < MAXTT; ++tt) {
+                if (tt < live) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int t = 8 * (tt0 + tt) + 2 * k.q + e;
+                        if (rok && t < T) {
+                            if (upart) {
+                                const size_t idx = (size_t)t * m + row;
+                                const double h = acc[tt][e];
+                                hu[idx] = h;
+                                if (MODE == 1) du[idx] = -(rdu[idx] - h) * w[idx];
+                            } else {
+                                const size_t idx = (size_t)t * n + row;
+                                double h = k.Xs[(size_t)t * k.ld + row] - acc[tt][e];      // v_t - A1' v_{t+1} - A2' v_{t+2}
+                                if (k.has_xf && t == T - 1) h += vglob[(size_t)T * n + row];
+                                hx[idx] = h;
+                                if (MODE == 1) dx[idx] = -(rdx[idx] + h) * __ldg((t == T - 1 ? S.qif : S.qi) + row);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Stage an x-like global array (rows of n) into Xs with a row offset: Xs row rr <- src row rr - shift.
+__device__ __forceinline__ void stage_rows(const KC &k, const double *src, int nrows, int shift)
+{
+    const int tot = (k.TP + 2) * k.ld;
+    for (int e = k.tid; e < tot; e += NTHREADS) {
+        const int rr = e / k.ld, c = e - rr * k.ld, sr = rr - shift;
+        k.Xs[e] = (sr >= 0 && sr < nrows && c < k.n) ? src[(size_t)sr * k.n + c] : 0.0;
+    }
 }
 
 } // namespace
 
 // =============================================================================================
-__global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSys S, const StepArgs A)
+template <int NP>
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(const DevSys S, const StepArgs A)
 {
     extern __shared__ double smem[];
     const int n = S.n, m = S.m, T = S.T;
     const int NB = T + (A.has_xf ? 1 : 0);
-    const Geom G = Geom::make(n, m);
+    const Geom G = Geom::make(n, m, T);
     const int ld = G.ld, KP = G.KP, RP = G.RP, nt = G.nt, ks = G.ks, lds = G.lds;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int gq = lane >> 2, q = lane & 3;                 // DMMA fragment coordinates
-    const Ctx c{S, n, m, T, NB, tid, nthr};
     const WsLayout L = WsLayout::make(n, m, T);
+    const int Mp = S.Mp, mp = S.mp, ldp = G.ldp, TP = G.TP;
 
-    double *ops = smem;                                     // 6 operand blocks | W chunk of the G*W GEMM
-    size_t opsz = 6 * G.blk();
-    if ((size_t)TCHUNK * G.ldp > opsz) opsz = (size_t)TCHUNK * G.ldp;
-    double *bS = smem + opsz;                               // RP x lds
-    double *sm_rhs = bS + (size_t)RP * lds;                 // 32
+    double *ops = smem;                                     // 5 operand blocks | staging (Us + Xs)
+    double *Us = ops, *Xs = ops + (size_t)TP * ldp;
+    double *sm_rhs = smem + G.ops_doubles();                // 32
     double *sm_y1 = sm_rhs + 32, *sm_y2 = sm_y1 + 32;       // y_{i-1}, y_{i-2}
     double *colbuf = sm_y2 + 32;                            // 64
     double *rsv = colbuf + 64;                              // 32
-    double *red = rsv + 32;                                 // 34
+    double *red = rsv + 32;                                 // 36
     __shared__ int s_inst, s_flag;
+    const KC kc{S, n, m, T, NB, A.has_xf, tid, lane, wid, gq, q, ld, nt, ks, mp, ldp, TP, G.ntt, Us, Xs, red};
 
     double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
-    double *nu = ws + L.nu, *dnu = ws + L.dnu, *yv = ws + L.yv, *rp = ws + L.rp, *rpt = ws + L.rpt, *bv = ws + L.bv;
+    double *nu = ws + L.nu, *dnu = ws + L.dnu, *yv = ws + L.yv, *bv = ws + L.bv;
+    double *rp = ws + L.rp, *rpt = ws + L.rpt;
     double *hx = ws + L.hx, *hdx = ws + L.hdx, *dx = ws + L.dx, *xt = ws + L.xt, *rdx = ws + L.rdx;
     double *hu = ws + L.hu, *hdu = ws + L.hdu, *du = ws + L.du, *ut = ws + L.ut, *dbar = ws + L.dbar;
     double *pinv = ws + L.pinv, *rdu = ws + L.rdu;
     double *gLi = ws + L.Lf, *gL1 = ws + L.L1, *gL2 = ws + L.L2, *Dsc = ws + L.Dsc;
     const size_t nn = (size_t)n * n;
-    const int Mp = S.Mp, mp = S.mp, ldp = G.ldp;
+    const int usp = TP * ldp;                               // padded u-space
+    const int xsp = (TP + 2) * ld;                          // padded x-space (staged rows)
 
     for (;;) {
         __syncthreads();
@@ -173,34 +350,50 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
         const int b = s_inst;
         if (b >= A.nbatch) break;
 
-        double *u = A.U + (size_t)b * m * T;
-        double *x = A.X + (size_t)b * n * T;
+        double *uo = A.U + (size_t)b * m * T, *xo = A.X + (size_t)b * n * T;      // output arrays
+        double *u = uo, *x = xo;                                                    // current iterate (ping-pongs with ut / xt)
+        double *un = ut, *xn = xt;
+        rp = ws + L.rp; rpt = ws + L.rpt;
         const double *x0 = A.x0 + (size_t)b * n;
         const double *x0p = A.x0_pre ? A.x0_pre + (size_t)b * n : nullptr;
 
-        // ---- initial iterate (fast_mpc_init.m:12-26), nu, b (fast_mpc_eq_const.m:39,44,47,68) ----
-        if (A.cold) {
-            for (int e = tid; e < T * m; e += nthr) { const int j = e % m; u[e] = (S.umin[j] + S.umax[j]) / 2; }
-            for (int e = tid; e < T * n; e += nthr) { const int k = e % n; x[e] = (S.xmin[k] + S.xmax[k]) / 2; }
-        } else if (A.U0 != A.U || A.X0 != A.X) {
-            const double *u0 = A.U0 + (size_t)b * m * T, *xx0 = A.X0 + (size_t)b * n * T;
-            for (int e = tid; e < T * m; e += nthr) u[e] = u0[e];
-            for (int e = tid; e < T * n; e += nthr) x[e] = xx0[e];
+        // ---- initial iterate (fast_mpc_init.m:12-26) staged straight into Us / Xs; nu; b (eq_const.m:39,44,47,68) ----
+        {
+            const double *u0 = A.cold ? nullptr : A.U0 + (size_t)b * m * T;
+            const double *xx0 = A.cold ? nullptr : A.X0 + (size_t)b * n * T;
+            for (int e = tid; e < usp; e += NTHREADS) {
+                const int t = e / ldp, j = e - t * ldp;
+                double v = 0.0;
+                if (t < T && j < m) {
+                    v = A.cold ? (S.umin[j] + S.umax[j]) / 2 : u0[(size_t)t * m + j];
+                    u[(size_t)t * m + j] = v;
+                }
+                Us[e] = v;
+            }
+            for (int e = tid; e < xsp; e += NTHREADS) {
+                const int rr = e / ld, k = e - rr * ld, sr = rr - 2;
+                double v = 0.0;
+                if (sr >= 0 && sr < T && k < n) {
+                    v = A.cold ? (S.xmin[k] + S.xmax[k]) / 2 : xx0[(size_t)sr * n + k];
+                    x[(size_t)sr * n + k] = v;
+                }
+                Xs[e] = v;
+            }
         }
-        for (int e = tid; e < NB * n; e += nthr) nu[e] = A.nu0[(size_t)b * NB * n + e];
-        for (int e = tid; e < NB * n; e += nthr) {
+        for (int e = tid; e < NB * n; e += NTHREADS) nu[e] = A.nu0[(size_t)b * NB * n + e];
+        for (int e = tid; e < NB * n; e += NTHREADS) {
             const int i = e / n, k = e - i * n;
             double v;
             if (i < T) {
                 v = A.w ? A.w[(size_t)b * T * n + e] : 0.0;
                 if (i == 0) {
                     double s = 0.0;
-                    for (int kk = 0; kk < n; ++kk) s = fma(S.A1[k + n * kk], x0[kk], s);
-                    if (S.has_a2) for (int kk = 0; kk < n; ++kk) s = fma(S.A2[k + n * kk], x0p[kk], s);
+                    for (int kk = 0; kk < n; ++kk) s = fma(__ldg(S.A1 + k + n * kk), x0[kk], s);
+                    if (S.has_a2) for (int kk = 0; kk < n; ++kk) s = fma(__ldg(S.A2 + k + n * kk), x0p[kk], s);
                     v += s;
                 } else if (i == 1 && S.has_a2) {
                     double s = 0.0;
-                    for (int kk = 0; kk < n; ++kk) s = fma(S.A2[k + n * kk], x0[kk], s);
+                    for (int kk = 0; kk < n; ++kk) s = fma(__ldg(S.A2 + k + n * kk), x0[kk], s);
                     v += s;
                 }
             } else {
@@ -209,74 +402,77 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
             bv[e] = v;
         }
         __syncthreads();
-        apply_Ct(c, nu, hu, hx);
-        apply_C_minus_b(c, u, x, bv, rp);
+        mma_apply_C(kc, bv, rp, false);                     // r_p = C z - b
+        __syncthreads();
+        stage_rows(kc, A.nu0 + (size_t)b * NB * n, T, 0);
+        __syncthreads();
+        mma_apply_Ct<0>(kc, nu, hu, hx, nullptr, nullptr, nullptr, nullptr, nullptr);
         __syncthreads();
 
         int status = ST_OK, iters = 0;
         for (int it = 0; it < A.niters; ++it) {
-            // ---- barrier terms (inf_newton_KKT_H.m:3-13) ----
-            for (int e = tid; e < T * m; e += nthr) {
-                const int j = e % m;
-                const double uu = u[e];
-                const double sp = S.umax[j] - uu, sm = -S.umin[j] + uu;
-                const double dp = 1.0 / sp, dm = 1.0 / sm;
-                dbar[e] = A.kappa * (dp - dm);
-                pinv[e] = 1.0 / (S.r2[j] + A.kappa * (dp * dp + dm * dm));
-            }
-            __syncthreads();
-            // ---- residuals + early exit (inf_newton_solver.m:12-22) ----
-            double ssp;
-            const double ss0 = resid_sumsq(c, u, x, hu, nullptr, hx, nullptr, 0.0, dbar, rp, red, rdu, rdx, &ssp);
-            const double nr0 = sqrt(ss0);
-            if (!isfinite(nr0)) { status = ST_NONFINITE; break; }
-            if (nr0 <= A.tol_r && sqrt(ssp) <= A.tol_p) { status = ST_EARLY_EXIT; break; }
-            __syncthreads();
-            // ---- beta = -r_p + C inv(Phi) r_d  (:28-29) ----
-            for (int e = tid; e < T * m; e += nthr) du[e] = rdu[e] * pinv[e];
-            for (int e = tid; e < T * n; e += nthr) {
-                const int jm1 = e / n, k = e - jm1 * n;
-                dx[e] = rdx[e] * ((jm1 == T - 1) ? S.qif[k] : S.qi[k]);
-            }
-            __syncthreads();
-            apply_C_minus_b(c, du, dx, rp, yv);             // yv = C p - r_p = beta
-            __syncthreads();
-            for (int e = tid; e < NB * n; e += nthr) yv[e] = -yv[e];   // rhs of  Y dnu = -beta
-
-            // ---- D_t = B diag(w_t) B' for all stages: Dsc(t, pair) = G * W, DMMA ----
-            for (int t0 = 0; t0 < T; t0 += TCHUNK) {
-                __syncthreads();
-                for (int e = tid; e < TCHUNK * mp; e += nthr) {
-                    const int tl = e / mp, j = e - tl * mp, t = t0 + tl;
-                    ops[tl * ldp + j] = (t < T && j < m) ? pinv[(size_t)t * m + j] : 0.0;
+            // ---- barrier terms (inf_newton_KKT_H.m:3-13), r_d (:12), p = inv(Phi) r_d staged for C p ----
+            double ssd = 0.0;
+            for (int e = tid; e < usp; e += NTHREADS) {
+                const int t = e / ldp, j = e - t * ldp;
+                double pv = 0.0;
+                if (t < T && j < m) {
+                    const size_t idx = (size_t)t * m + j;
+                    const double uu = u[idx];
+                    const double sp = __ldg(S.umax + j) - uu, sm = -__ldg(S.umin + j) + uu;
+                    const double dp = 1.0 / sp, dm = 1.0 / sm;
+                    const double db = A.kappa * (dp - dm);
+                    const double w = 1.0 / (__ldg(S.r2 + j) + A.kappa * (dp * dp + dm * dm));
+                    const double r = rdu_expr(__ldg(S.r2 + j), __ldg(S.rl + j), uu, hu[idx], db);
+                    dbar[idx] = db; pinv[idx] = w; rdu[idx] = r;
+                    ssd = fma(r, r, ssd);
+                    pv = r * w;
                 }
-                __syncthreads();
-                const int ntt = min(TCHUNK / 8, (T - t0 + 7) / 8);
-                const int kst = mp / 4;
-                for (int g = wid; g < Mp / 8; g += NWARPS) {
-                    double acc[TCHUNK / 8][2];
+                Us[e] = pv;
+            }
+            for (int e = tid; e < xsp; e += NTHREADS) {
+                const int rr = e / ld, k = e - rr * ld, sr = rr - 2;
+                double pv = 0.0;
+                if (sr >= 0 && sr < T && k < n) {
+                    const size_t idx = (size_t)sr * n + k;
+                    const bool last = (sr == T - 1);
+                    const double r = rdx_expr(__ldg((last ? S.q2f : S.q2) + k), __ldg((last ? S.qfl : S.ql) + k), x[idx], hx[idx]);
+                    rdx[idx] = r;
+                    ssd = fma(r, r, ssd);
+                    pv = r * __ldg((last ? S.qif : S.qi) + k);
+                }
+                Xs[e] = pv;
+            }
+            double ssp = 0.0;
+            for (int e = tid; e < NB * n; e += NTHREADS) ssp = fma(rp[e], rp[e], ssp);
+            const double tot_p = block_sum(ssp, red);
+            const double tot_d = block_sum(ssd, red);
+            const double nr0 = sqrt(tot_d + tot_p);
+            // ---- early exit (inf_newton_solver.m:19-22) ----
+            if (!isfinite(nr0)) { status = ST_NONFINITE; break; }
+            if (nr0 <= A.tol_r && sqrt(tot_p) <= A.tol_p) { status = ST_EARLY_EXIT; break; }
+            // ---- rhs of  Y dnu = -beta,  beta = -r_p + C inv(Phi) r_d  (:28-29) ----
+            mma_apply_C(kc, rp, yv, true);
+            __syncthreads();
+
+            // ---- D_t = B diag(w_t) B' for all stages: Dsc(t, pair) = G * W ----
+            for (int e = tid; e < usp; e += NTHREADS) {
+                const int t = e / ldp, j = e - t * ldp;
+                Us[e] = (t < T && j < m) ? pinv[(size_t)t * m + j] : 0.0;
+            }
+            __syncthreads();
+            for (int g = wid; g < Mp / 8; g += NWARPS) {
+                for (int tt0 = 0; tt0 < G.ntt; tt0 += MAXTT) {
+                    const int live = min(MAXTT, G.ntt - tt0);
+                    double acc[MAXTT][2];
 #pragma unroll
-                    for (int tt = 0; tt < TCHUNK / 8; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
-                    const double *Grow = S.G + (size_t)(8 * g + gq) * mp + q;
-                    const double *Wrow = ops + gq * ldp + q;
-                    for (int k0 = 0; k0 < kst; k0 += 12) {
-                        double af[12];
-#pragma unroll
-                        for (int kk = 0; kk < 12; ++kk) af[kk] = (k0 + kk < kst) ? __ldg(Grow + 4 * (k0 + kk)) : 0.0;
-#pragma unroll
-                        for (int kk = 0; kk < 12; ++kk) {
-                            if (k0 + kk < kst) {
-#pragma unroll
-                                for (int tt = 0; tt < TCHUNK / 8; ++tt)
-                                    if (tt < ntt) dmma(acc[tt][0], acc[tt][1], af[kk], Wrow[(size_t)(8 * tt) * ldp + 4 * (k0 + kk)]);
-                            }
-                        }
-                    }
+                    for (int tt = 0; tt < MAXTT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+                    mma_gA_sB(acc, S.G + (size_t)(8 * g + gq) * mp + q, true, mp, mp / 4, Us + (size_t)(8 * tt0 + gq) * ldp + q, ldp, live, q);
                     const int pair = 8 * g + gq;
 #pragma unroll
-                    for (int tt = 0; tt < TCHUNK / 8; ++tt) {
-                        const int t = t0 + 8 * tt + 2 * q;
-                        if (tt < ntt) {
+                    for (int tt = 0; tt < MAXTT; ++tt) {
+                        const int t = 8 * (tt0 + tt) + 2 * q;
+                        if (tt < live) {
                             if (t < T) Dsc[(size_t)t * Mp + pair] = acc[tt][0];
                             if (t + 1 < T) Dsc[(size_t)(t + 1) * Mp + pair] = acc[tt][1];
                         }
@@ -285,17 +481,19 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
             }
             __syncthreads();
             // zero the operand blocks (padding rows / columns must stay exactly zero)
-            for (int e = tid; e < (int)(6 * G.blk()); e += nthr) ops[e] = 0.0;
+            for (int e = tid; e < (int)(5 * G.blk()); e += NTHREADS) ops[e] = 0.0;
             __syncthreads();
 
             // ---- band-2 block Cholesky of Y fused with the forward solve (:30-31) ----
+            // five blocks: Linv (doubles as S scratch), L1 ring x2, L2 ring x2 (the older one doubles as U scratch)
             double *bLinv = ops, *bM1 = ops + G.blk(), *bL1p = ops + 2 * G.blk();
-            double *bM2 = ops + 3 * G.blk(), *bL2p = ops + 4 * G.blk(), *bL2pp = ops + 5 * G.blk();
+            double *bL2p = ops + 3 * G.blk(), *bL2pp = ops + 4 * G.blk();
             bool fail = false;
             const int nS = nt * (nt + 1) / 2;
             for (int i = 0; i < NB; ++i) {
                 const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && S.has_a2;
                 const bool up1 = (i >= 1), up2 = (i >= 2) && S.has_a2;
+                double *bS = bLinv;                          // inv(L_{i-1}) is dead: its block receives S_i
                 // -- phase 1: S (lower tiles) and M1 tiles --
                 const double *Yd = S.ypool + (size_t)S.ydi[i] * nn;
                 const int y1 = S.y1i[i];
@@ -308,8 +506,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
                         const int r = 8 * rt + gq, cc = 8 * ct + 2 * q;
                         double i0 = 0.0, i1 = 0.0;
                         if (r < n) {
-                            if (cc <= r) { i0 = Yd[r * n + cc]; if (i < T) i0 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc]; }
-                            if (cc + 1 <= r) { i1 = Yd[r * n + cc + 1]; if (i < T) i1 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc + 1]; }
+                            if (cc <= r) { i0 = __ldg(Yd + r * n + cc); if (i < T) i0 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc]; }
+                            if (cc + 1 <= r) { i1 = __ldg(Yd + r * n + cc + 1); if (i < T) i1 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc + 1]; }
                         }
                         double p0 = 0.0, p1 = 0.0;
                         if (up1) tile_nt(p0, p1, bL1p + (8 * rt + gq) * ld + q, bL1p + (8 * ct + gq) * ld + q, ks);
@@ -323,8 +521,8 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
                         const int r = 8 * rt + gq, cc = 8 * ct + 2 * q;
                         double i0 = 0.0, i1 = 0.0;
                         if (r < n && y1 >= 0) {
-                            if (cc < n) i0 = S.ypool[(size_t)y1 * nn + r * n + cc];
-                            if (cc + 1 < n) i1 = S.ypool[(size_t)y1 * nn + r * n + cc + 1];
+                            if (cc < n) i0 = __ldg(S.ypool + (size_t)y1 * nn + r * n + cc);
+                            if (cc + 1 < n) i1 = __ldg(S.ypool + (size_t)y1 * nn + r * n + cc + 1);
                         }
                         double p0 = 0.0, p1 = 0.0;
                         if (up1 && S.has_a2) tile_nt(p0, p1, bL2p + (8 * rt + gq) * ld + q, bL1p + (8 * ct + gq) * ld + q, ks);
@@ -345,14 +543,15 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
                     }
                 }
                 __syncthreads();
-                // -- phase 2: factor + invert the diagonal block (warp 0) --
-                if (wid == 0) {
-                    const int info = warp_potrf_inverse(bS, lds, bLinv, ld, KP, gLi + (size_t)i * nn, n, colbuf, rsv, lane);
+                // -- phase 2: factor + invert the diagonal block (one warp, rotating over the SM sub-partitions) --
+                if (wid == (i & (NWARPS - 1))) {
+                    const int info = warp_potrf_inverse<NP>(bS, bL2pp, bLinv, ld, gLi + (size_t)i * nn, n, colbuf, rsv, lane);
                     if (lane == 0) s_flag = info;
                 }
                 __syncthreads();
                 if (s_flag) { fail = true; break; }
-                // -- phase 3: L1_i = M1 inv(L)' (in place), L2_i = Y2 inv(L)', y_i = inv(L) rhs --
+                // -- phase 3: L1_i = M1 inv(L)' (in place), L2_i = Y2 inv(L)' (into the dead L2pp block), y_i = inv(L) rhs --
+                double *bM2 = bL2pp;
                 for (int rt = wid; rt < nt; rt += NWARPS) {
                     const int r = 8 * rt + gq;
                     if (has1) {
@@ -397,6 +596,13 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
                                 if (cc + 1 < n) gL2[(size_t)i * nn + r * n + cc + 1] = c1;
                             }
                         }
+                    } else {
+                        // the block held the U scratch of the factorization: restore the zero padding invariant
+                        for (int ct = 0; ct < nt; ++ct) {
+                            const int cc = 8 * ct + 2 * q;
+                            if (cc < KP) bM2[r * ld + cc] = 0.0;
+                            if (cc + 1 < KP) bM2[r * ld + cc + 1] = 0.0;
+                        }
                     }
                 }
                 {
@@ -405,17 +611,16 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
                     if (r < RP) for (int k = q; k < KP; k += 4) s = fma(bLinv[r * ld + k], sm_rhs[k], s);
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
                     s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    __syncthreads();                               // everyone is done with sm_y1 / sm_y2 / bL*p of this stage
+                    __syncthreads();                               // everyone is done with sm_y1 / sm_y2 / the *p blocks of this stage
                     if (r < RP && q == 0) {
                         if (r < n) yv[i * n + r] = s;
                         sm_y2[r] = sm_y1[r];
-                        sm_y1[r] = s;
+                        sm_y1[r] = (r < n) ? s : 0.0;
                     }
                 }
-                {   // rotate: L2pp <- L2p, L2p <- M2, L1p <- M1 ; freed buffers become M1, M2
-                    double *oL1p = bL1p, *oL2pp = bL2pp;
-                    bL2pp = bL2p; bL2p = bM2; bL1p = bM1;
-                    bM1 = oL1p; bM2 = oL2pp;
+                {   // rotate the rings: L1p <-> M1 ; L2pp (now L2_i) becomes L2p, old L2p becomes L2pp
+                    double *t1 = bL1p; bL1p = bM1; bM1 = t1;
+                    double *t2 = bL2p; bL2p = bL2pp; bL2pp = t2;
                 }
                 __syncthreads();
             }
@@ -448,39 +653,69 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
             }
 
             // ---- dz = inv(Phi)(-r_d - C' dnu)  (:34-35) ----
-            apply_Ct(c, dnu, hdu, hdx);
+            stage_rows(kc, dnu, T, 0);
             __syncthreads();
-            for (int e = tid; e < T * m; e += nthr) du[e] = -(rdu[e] - hdu[e]) * pinv[e];
-            for (int e = tid; e < T * n; e += nthr) {
-                const int jm1 = e / n, k = e - jm1 * n;
-                dx[e] = -(rdx[e] + hdx[e]) * ((jm1 == T - 1) ? S.qif[k] : S.qi[k]);
-            }
+            mma_apply_Ct<1>(kc, dnu, hdu, hdx, rdu, rdx, pinv, du, dx);
             __syncthreads();
 
             // ---- backtracking on ||[r_p; r_d]||, d frozen (backtracking_inf_newton.m:2-11) ----
             double t = 1.0;
             int nh = 0;
             for (;;) {
-                for (int e = tid; e < T * m; e += nthr) ut[e] = __fma_rn(t, du[e], u[e]);
-                for (int e = tid; e < T * n; e += nthr) xt[e] = __fma_rn(t, dx[e], x[e]);
+                // trial point staged for C z_t; dual residual with the SAME expressions / summation order as above
+                double sst = 0.0;
+                for (int e = tid; e < usp; e += NTHREADS) {
+                    const int tt = e / ldp, j = e - tt * ldp;
+                    double uv = 0.0;
+                    if (tt < T && j < m) {
+                        const size_t idx = (size_t)tt * m + j;
+                        uv = __fma_rn(t, du[idx], u[idx]);
+                        un[idx] = uv;
+                        const double r = rdu_expr(__ldg(S.r2 + j), __ldg(S.rl + j), uv, __fma_rn(t, hdu[idx], hu[idx]), dbar[idx]);
+                        sst = fma(r, r, sst);
+                    }
+                    Us[e] = uv;
+                }
+                for (int e = tid; e < xsp; e += NTHREADS) {
+                    const int rr = e / ld, k = e - rr * ld, sr = rr - 2;
+                    double xv = 0.0;
+                    if (sr >= 0 && sr < T && k < n) {
+                        const size_t idx = (size_t)sr * n + k;
+                        const bool last = (sr == T - 1);
+                        xv = __fma_rn(t, dx[idx], x[idx]);
+                        xn[idx] = xv;
+                        const double r = rdx_expr(__ldg((last ? S.q2f : S.q2) + k), __ldg((last ? S.qfl : S.ql) + k), xv,
+                                                  __fma_rn(t, hdx[idx], hx[idx]));
+                        sst = fma(r, r, sst);
+                    }
+                    Xs[e] = xv;
+                }
                 __syncthreads();
-                apply_C_minus_b(c, ut, xt, bv, rpt);
+                mma_apply_C(kc, bv, rpt, false);
                 __syncthreads();
-                const double sst = resid_sumsq(c, ut, xt, hu, hdu, hx, hdx, t, dbar, rpt, red, nullptr, nullptr, nullptr);
-                const double nrt = sqrt(sst);
+                double sspt = 0.0;
+                for (int e = tid; e < NB * n; e += NTHREADS) sspt = fma(rpt[e], rpt[e], sspt);
+                const double tp = block_sum(sspt, red);
+                const double td = block_sum(sst, red);
+                const double nrt = sqrt(td + tp);
                 if (!(nrt > (1.0 - A.alpha * t) * nr0)) break;
                 if (t == 0.0) break;
                 if (A.ls_max > 0 && nh >= A.ls_max) { status = ST_LS_MAX; break; }
                 t *= A.beta;
                 ++nh;
-                __syncthreads();
             }
-            __syncthreads();
-            for (int e = tid; e < T * m; e += nthr) { u[e] = ut[e]; hu[e] = __fma_rn(t, hdu[e], hu[e]); }
-            for (int e = tid; e < T * n; e += nthr) { x[e] = xt[e]; hx[e] = __fma_rn(t, hdx[e], hx[e]); }
-            for (int e = tid; e < NB * n; e += nthr) { nu[e] = __fma_rn(t, dnu[e], nu[e]); rp[e] = rpt[e]; }
+            // accept: swap iterate / r_p buffers, advance the dual images
+            { double *s1 = u; u = un; un = s1; double *s2 = x; x = xn; xn = s2; double *s3 = rp; rp = rpt; rpt = s3; }
+            for (int e = tid; e < T * m; e += NTHREADS) hu[e] = __fma_rn(t, hdu[e], hu[e]);
+            for (int e = tid; e < T * n; e += NTHREADS) hx[e] = __fma_rn(t, hdx[e], hx[e]);
+            for (int e = tid; e < NB * n; e += NTHREADS) nu[e] = __fma_rn(t, dnu[e], nu[e]);
             ++iters;
             __syncthreads();
+        }
+        __syncthreads();
+        if (u != uo) {                                       // the iterate ended in the scratch buffers
+            for (int e = tid; e < T * m; e += NTHREADS) uo[e] = u[e];
+            for (int e = tid; e < T * n; e += NTHREADS) xo[e] = x[e];
         }
         if (tid == 0) {
             if (A.status) A.status[b] = status;
@@ -491,28 +726,46 @@ __global__ void __launch_bounds__(NTHREADS, 4) fmpc_solve_kernel_mma(const DevSy
 }
 
 // =============================================================================================
+template <int NP>
+static int config_np(const Geom &G, SolveLaunchCfg *cfg, int sms)
+{
+    const size_t smem = G.smem_doubles() * sizeof(double);
+    if (cudaFuncSetAttribute(fmpc_solve_kernel_mma<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_mma<NP>, NTHREADS, smem) != cudaSuccess || per_sm < 1)
+        return -5;
+    if (const char *e = getenv("FMPC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
+    cfg->grid = sms * per_sm;
+    cfg->block = NTHREADS;
+    cfg->smem = smem;
+    cfg->use_mma = NP;
+    return 0;
+}
+
 int fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg)
 {
     if (S.n > 32) return -1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
-    const Geom G = Geom::make(S.n, S.m);
-    const size_t smem = G.smem_doubles() * sizeof(double);
-    if (smem > (size_t)prop.sharedMemPerBlockOptin) return -3;
-    if (cudaFuncSetAttribute(fmpc_solve_kernel_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_mma, NTHREADS, smem) != cudaSuccess || per_sm < 1)
-        return -5;
-    cfg->grid = prop.multiProcessorCount * per_sm;
-    cfg->block = NTHREADS;
-    cfg->smem = smem;
-    cfg->use_mma = 1;
-    return 0;
+    const Geom G = Geom::make(S.n, S.m, S.T);
+    if (G.smem_doubles() * sizeof(double) > (size_t)prop.sharedMemPerBlockOptin) return -3;
+    switch (G.KP) {
+    case 8: return config_np<8>(G, cfg, prop.multiProcessorCount);
+    case 16: return config_np<16>(G, cfg, prop.multiProcessorCount);
+    case 28: return config_np<28>(G, cfg, prop.multiProcessorCount);
+    default: return config_np<32>(G, cfg, prop.multiProcessorCount);
+    }
 }
 
 void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream)
 {
     int grid = cfg.grid < A.nbatch ? cfg.grid : A.nbatch;
     if (grid < 1) grid = 1;
-    fmpc_solve_kernel_mma<<<grid, cfg.block, cfg.smem, (cudaStream_t)stream>>>(S, A);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cfg.use_mma) {
+    case 8: fmpc_solve_kernel_mma<8><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
+    case 16: fmpc_solve_kernel_mma<16><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
+    case 28: fmpc_solve_kernel_mma<28><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
+    default: fmpc_solve_kernel_mma<32><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
+    }
 }
