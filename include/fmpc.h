@@ -179,6 +179,9 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K,
                      const double *a, const double *nu0,
                      double *U_acc, double *X_acc, int *iters_acc, double *telapsed);
 
+/* Dimensions the handle was created with (any pointer may be NULL). */
+int fmpc_get_dims(const fmpc_handle *h, int *n, int *m, int *T);
+
 /* Device-resident workspace access for benchmarks / pipelines: size in bytes the handle holds. */
 long long fmpc_workspace_bytes(const fmpc_handle *h);
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */

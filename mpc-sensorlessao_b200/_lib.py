@@ -42,7 +42,7 @@ class FmpcParams(C.Structure):
 ABI_SYMBOLS = [
     "fmpc_default_params", "fmpc_device_count", "fmpc_create", "fmpc_destroy", "fmpc_step", "fmpc_step_d",
     "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
-    "fmpc_closed_loop", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_strerror",
+    "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_strerror",
     "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
 ]

@@ -363,6 +363,15 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     return FMPC_OK;
 }
 
+int fmpc_get_dims(const fmpc_handle *h, int *n, int *m, int *T)
+{
+    if (!h) return FMPC_ERR_NULL;
+    if (n) *n = h->n;
+    if (m) *m = h->m;
+    if (T) *T = h->T;
+    return FMPC_OK;
+}
+
 long long fmpc_workspace_bytes(const fmpc_handle *h) { return h ? (long long)h->ws.bytes : 0; }
 long long fmpc_launch_count(const fmpc_handle *h) { return h ? h->launches : 0; }
 

@@ -42,6 +42,14 @@ def test_header_compiles_as_plain_c(tmp_path):
                            "-o", str(tmp_path / "t.o")])
 
 
+def test_mex_shim_compiles_against_the_header():
+    """The MATLAB gateway cannot be linked here (no MATLAB): compile-check it against a stub mex.h so it stays in
+    sync with include/fmpc.h."""
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "stubs"),
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "mpc-sensorlessao_b200", "matlab", "fmpc_mex.c")])
+
+
 def test_sass_is_sm100_only(pk):
     out = subprocess.run(["cuobjdump", "-lelf", pk.lib_path()], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
