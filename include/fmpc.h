@@ -189,6 +189,13 @@ long long fmpc_launch_count(const fmpc_handle *h);
 /* Total Newton iterations executed by the last fmpc_step* call on this handle (sum over instances);
  * requires a device sync, so call it outside timed regions. */
 long long fmpc_last_newton_iters(fmpc_handle *h);
+/* Which solve kernel the handle selected: 2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA-per-instance
+ * DMMA kernel (experiments), 0 = generic kernel (any n). */
+int fmpc_kernel_kind(const fmpc_handle *h);
+/* Phase cycle counters of the last solve launch, summed over warps (all zero unless the library was
+ * built with -DFMPC_PROF): init, newton pass, forward sweep, backward sweep, C' pass, line search,
+ * accept, copy-out, 4 spare. */
+int fmpc_last_profile(fmpc_handle *h, long long *out12);
 
 const char *fmpc_strerror(int code);
 

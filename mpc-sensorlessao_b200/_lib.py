@@ -7,7 +7,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "lib", "libfmpc_b200.so")
+# FMPC_B200_LIB selects an alternative BUILD of the same library (e.g. the -DFMPC_PROF profiling variant); never a fallback
+_SO = os.environ.get("FMPC_B200_LIB") or os.path.join(_HERE, "lib", "libfmpc_b200.so")
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
 
@@ -42,7 +43,7 @@ class FmpcParams(C.Structure):
 ABI_SYMBOLS = [
     "fmpc_default_params", "fmpc_device_count", "fmpc_create", "fmpc_destroy", "fmpc_step", "fmpc_step_d",
     "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
-    "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_strerror",
+    "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
     "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
 ]
@@ -93,6 +94,8 @@ def load_library():
     for f in ("fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "zmf_launch_count"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_longlong
+    L.fmpc_kernel_kind.argtypes = [vp]
+    L.fmpc_last_profile.argtypes = [vp, vp]
     L.fmpc_strerror.argtypes = [C.c_int]
     L.fmpc_strerror.restype = C.c_char_p
     L.fmpc_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_int]

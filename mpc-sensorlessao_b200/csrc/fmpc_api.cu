@@ -346,15 +346,28 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     }
 #undef UP
     if (ok) {
-        const char *force_v1 = getenv("FMPC_FORCE_V1");
-        if ((force_v1 && force_v1[0] == '1') || fmpc_mma_config(S, device, &h->cfg) != 0) {
+        // kernel selection: warp-per-instance DMMA kernel (n <= 32) > CTA DMMA kernel (experiments only) > generic
+        const char *force = getenv("FMPC_FORCE_KERNEL");       // "v1" | "v2" : A/B experiments
+        const bool want_v1 = force && force[0] == 'v' && force[1] == '1';
+        const bool want_v2 = force && force[0] == 'v' && force[1] == '2';
+        const WsLayout L = WsLayout::make(n, m, T);
+        int rc2 = -1;
+        if (!want_v1 && !want_v2) rc2 = fmpc_warp_config(S, device, &h->cfg);
+        if (rc2 != 0 && !want_v1) {
+            rc2 = fmpc_mma_config(S, device, &h->cfg);
+            if (rc2 == 0) { h->cfg.slots = h->cfg.grid; h->cfg.ws_stride = L.total; }
+        }
+        if (rc2 != 0) {
             if (fmpc_solve_config(S, device, &h->cfg) != 0) ok = false;
+            else { h->cfg.slots = h->cfg.grid; h->cfg.ws_stride = L.total; }
         }
     }
     if (ok) {
-        const WsLayout L = WsLayout::make(n, m, T);
-        h->ws_stride = L.total;
-        if (h->ws.ensure((size_t)h->cfg.grid * L.total * sizeof(double)) || h->counters.ensure(64)) ok = false;
+        h->ws_stride = h->cfg.ws_stride;
+        const size_t wsb = (size_t)h->cfg.slots * h->cfg.ws_stride * sizeof(double);
+        if (h->ws.ensure(wsb) || h->counters.ensure(256)) ok = false;
+        // the warp kernel relies on never-written padding columns of its scratch staying zero
+        if (ok && cudaMemset(h->ws.p, 0, wsb) != cudaSuccess) ok = false;
     }
     if (ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
     if (ok && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) ok = false;
@@ -374,6 +387,17 @@ int fmpc_get_dims(const fmpc_handle *h, int *n, int *m, int *T)
 
 long long fmpc_workspace_bytes(const fmpc_handle *h) { return h ? (long long)h->ws.bytes : 0; }
 long long fmpc_launch_count(const fmpc_handle *h) { return h ? h->launches : 0; }
+
+int fmpc_kernel_kind(const fmpc_handle *h) { return h ? h->cfg.use_mma : -1; }
+
+int fmpc_last_profile(fmpc_handle *h, long long *out12)
+{
+    if (!h || !out12) return FMPC_ERR_NULL;
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return FMPC_ERR_CUDA;
+    if (cudaMemcpy(out12, h->counters.as<char>() + 64, 12 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return FMPC_ERR_CUDA;
+    return FMPC_OK;
+}
 
 long long fmpc_last_newton_iters(fmpc_handle *h)
 {
@@ -398,8 +422,10 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     A.counter = h->counters.as<unsigned int>();
     A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
-    CU_OK(cudaMemsetAsync(h->counters.p, 0, 16, st));
-    if (h->cfg.use_mma) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
+    A.prof = (long long *)(h->counters.as<char>() + 64);
+    CU_OK(cudaMemsetAsync(h->counters.p, 0, 256, st));
+    if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, h->cfg, st);
+    else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
     else fmpc_launch_solve(h->S, A, h->cfg, st);
     CU_OK(cudaGetLastError());
     h->launches += 1;

@@ -42,8 +42,9 @@ struct StepArgs {
     int *status, *iters;
     unsigned int *counter;              // dynamic instance counter (zeroed before launch)
     unsigned long long *iters_total;    // sum of Newton iterations (zeroed before launch)
-    double *ws;                         // per-CTA scratch
-    size_t ws_stride;                   // doubles per CTA
+    double *ws;                         // per-slot scratch (slot = CTA for the CTA kernels, warp for the warp kernel)
+    size_t ws_stride;                   // doubles per slot
+    long long *prof;                    // optional phase-cycle accumulators (builds with -DFMPC_PROF), else NULL
 };
 
 // Per-CTA scratch layout (in doubles), computed identically on host and device.
@@ -73,7 +74,8 @@ struct WsLayout {
 // status words (mirror include/fmpc.h)
 enum { ST_OK = 0, ST_EARLY_EXIT = 1, ST_NOT_PD = 2, ST_LS_MAX = 3, ST_NONFINITE = 4 };
 
-struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; };
+// use_mma: 0 = generic CTA kernel (any n), 1 = CTA-per-instance DMMA kernel (n <= 32), 2 = warp-per-instance DMMA kernel (n <= 32)
+struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; int slots; size_t ws_stride; };
 
 // kernels.cu
 int  fmpc_solve_config(const DevSys &S, int device, SolveLaunchCfg *cfg);        // 0 ok
@@ -86,3 +88,7 @@ void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int 
 // kernel_mma.cu : DMMA path (n <= 32)
 int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable
 void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
+
+// kernel_warp.cu : warp-per-instance DMMA path (n <= 32), the default
+int  fmpc_warp_config(const DevSys &S, int device, SolveLaunchCfg *cfg);         // 0 ok, <0 not applicable
+void fmpc_launch_solve_warp(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);

@@ -135,6 +135,17 @@ class FastMPCBatch:
     def last_newton_iters(self) -> int:
         return int(self._L.fmpc_last_newton_iters(self._h))
 
+    @property
+    def kernel_kind(self) -> int:
+        """2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA DMMA kernel, 0 = generic kernel."""
+        return int(self._L.fmpc_kernel_kind(self._h))
+
+    def last_profile(self):
+        """Phase cycle counters of the last launch (zeros unless built with -DFMPC_PROF)."""
+        out = np.zeros(12, dtype=np.int64)
+        check(self._L.fmpc_last_profile(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # ---- batched solve -------------------------------------------------------------------
     def step(self, x0, x0_pre=None, w=None, xf=None, X0=None, U0=None, nu0=None, u_prev=None, params=None,
              kappa=0.01, niters=5, ls_max=0, frontend=None, k_min=None, k_max=None):
