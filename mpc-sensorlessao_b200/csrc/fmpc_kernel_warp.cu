@@ -4,24 +4,26 @@
 // (inf_newton_solver.m:10-41 on the block structure of DESIGN.md section 2).  Nothing in the solve needs
 // a CTA barrier: the warps of a CTA only share the problem constants (B, A1, A2, bounds, weights) that
 // are staged once in shared memory.  Every dense contraction is an FP64 tensor-pipe instruction
-// (mma.sync.aligned.m8n8k4.f64 = DMMA):
+// (mma.sync.aligned.m8n8k4.f64 = DMMA); on sm_100a DMMA and DFMA share one FP64 pipe per SM sub-partition
+// (profiles/r01_ubench_fp64_pipes_latency.log), so scalar FP64 work is kept to the barrier terms and the
+// 8 x 8 diagonal blocks.
 //   * C z, C inv(Phi) r_d and the trial residuals are horizon GEMMs  [T x (m+2n)] * [(m+2n) x n]  with
 //     the stage index as the M dimension; the barrier terms / trial point are computed by the thread
-//     that owns the A-fragment element, in registers, straight from global memory (no staging);
+//     that owns the A-fragment element, in registers, straight from global memory (software pipelined);
 //   * C' v is the transposed pair  [T x n] * [n x m],  [T x n] * [n x n];
-//   * band-2 block Cholesky of Y = C inv(Phi) C' per stage i:
-//       S_i  = Yd_i + B diag(w_i) B' - L1_{i-1} L1_{i-1}' - L2_{i-2} L2_{i-2}'     (lower tiles, registers)
-//       L_i  = chol(S_i), inv(L_i)                                                  (one warp, registers)
-//       L1_i = (Y1_i - L2_{i-1} L1_{i-1}') inv(L_i)' ,  L2_i = Y2 inv(L_i)'
-//     The accumulator tiles of (Y1 - L2 L1') are fed back as the A operand of the next product without
-//     leaving registers (the k index of an m8n8k4 contraction may be permuted freely, and the
-//     accumulator layout {row gq, cols 2q, 2q+1} is a valid A layout for k = {2q+e}); inv(L_i) is stored
-//     in that fragment order.  The forward substitution costs nothing: row n of every block (a padding
-//     row of the last 8-row tile) carries y_{i-1}', so rhs_i and y_i = inv(L_i) rhs_i fall out of the
-//     same tiles.
+//   * band-2 block Cholesky of Y = C inv(Phi) C' per stage i, entirely in registers:
+//       S_i  = Yd_i + B diag(w_i) B' - L1_{i-1} L1_{i-1}' - L2_{i-2} L2_{i-2}'     (lower 8x8 tiles, accumulators)
+//       L_i  = chol(S_i), inv(L_i): blocked right-looking on the accumulator tiles.  A tile in accumulator
+//              layout {row gq, cols 2q, 2q+1} is at the same time a valid A operand (k = 2q+e) and a valid B
+//              operand of X T' (n = gq, k = 2q+e), so panel solves, trailing updates and the triangular
+//              inverse are DMMAs on registers; only the 8x8 diagonal blocks are factored/inverted with
+//              shuffles.  The right-hand side rides along as one more row of S (row n), so the forward
+//              substitution y_i = inv(L_i) rhs_i falls out of the panel operations.
+//       L1_i = (Y1_i - L2_{i-1} L1_{i-1}') inv(L_i)' ,  L2_i = Y2 inv(L_i)'         (X T' with T = inv(L) tiles)
 //   * the factor (inv(L_i), L1_i, L2_i) streams to a per-warp global scratch and comes back through a
-//     4-slot cp.async ring for the backward substitution.
-// Shared memory per warp: 3 history blocks + 1 work block + the staged w_i row; per CTA: the constants.
+//     cp.async ring for the backward substitution.
+// Shared memory per warp: 3 history blocks (L1_{i-1}, L2_{i-1}, L2_{i-2}; row n of each carries y) + the
+// staged w_i rows; per CTA: the constants.  8 warps (= 8 instances) per SM.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -35,9 +37,13 @@ constexpr int TTMAX = 3;                 // 8-stage row tiles accumulated togeth
 #ifdef FMPC_PROF
 #define PROF_DECL long long p_acc[12]; long long p_last = clock64(); for (int i_ = 0; i_ < 12; ++i_) p_acc[i_] = 0;
 #define PROF_T(idx) do { const long long now_ = clock64(); p_acc[idx] += now_ - p_last; p_last = now_; } while (0)
+#define PROF_PARAMS , long long (&p_acc)[12], long long &p_last
+#define PROF_ARGS , p_acc, p_last
 #else
 #define PROF_DECL
 #define PROF_T(idx) do { } while (0)
+#define PROF_PARAMS
+#define PROF_ARGS
 #endif
 
 __device__ __forceinline__ void dmma(double (&c)[2], const double a, const double b)
@@ -45,10 +51,17 @@ __device__ __forceinline__ void dmma(double (&c)[2], const double a, const doubl
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
         : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
+// o += X T'   for 8 x 8 tiles X, T both in accumulator layout (k runs over {2q+e})
+__device__ __forceinline__ void mma_xt(double (&o)[2], const double (&x)[2], const double (&t)[2])
+{
+    dmma(o, x[0], t[0]);
+    dmma(o, x[1], t[1]);
+}
 __device__ __forceinline__ double dneg(const double x)
 {
     return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
 }
+__device__ __forceinline__ double shfl_d(const double v, const int src) { return __shfl_sync(FULL, v, src); }
 // 1/x : MUFU.RCP64H seed + two Newton steps (<= 1 ulp for normal x of either sign).
 __device__ __forceinline__ double rcp_nr(const double x)
 {
@@ -59,14 +72,22 @@ __device__ __forceinline__ double rcp_nr(const double x)
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
+// 1/sqrt(x), x > 0 normal : MUFU.RSQ64H seed + two Newton steps
+__device__ __forceinline__ double rsqrt_nr(const double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __forceinline__ double ldp(const double *p, const bool ok) { return ok ? *p : 0.0; }
-
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -87,15 +108,20 @@ __device__ __forceinline__ double rdx_expr(double q2, double ql, double x, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// Geometry (host + device).  NPOT = compile-time size of the diagonal-block factorization,
-// CT = 8-column tiles, RT = 8-row tiles including the row that carries the forward substitution.
+// Geometry (host + device).  NPOT = padded block size (multiple of 4 = k-steps of the block products),
+// CT = 8-column tiles, RT = 8-row tiles including row n (the row that carries the forward substitution).
+// Conventions that let the operand loads run without predicates:
+//   * an operand row that does not exist (row > n of a block, row >= n of B / A1 / A2) only ever feeds an
+//     output row or column that is never used, so it may read whatever FINITE data follows in shared memory
+//     (all shared memory is zero-initialised and only finite values are ever stored);
+//   * the k (contraction) index is always < NPOT and padded with exact zeros on at least one side.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int npot_of(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 24 ? 24 : (n <= 28 ? 28 : 32))); }
 __host__ __device__ inline int ld_of(int npot) { return (npot % 8 == 4) ? npot : npot + 4; }
 
 struct WGeom {
-    int n, m, T, NPOT, CT, RT, KS, LD, BLK, WSZ, mpad, MK, MT8, npad, LDB, NTT, NN;
-    size_t const_doubles, warp_doubles;
+    int n, m, T, NPOT, CT, RT, KS, LD, BLK, WB, mpad, MK, MT8, npad, LDB, NTT, TP8, NN;
+    size_t const_doubles, warp_doubles, tail_doubles;
     __host__ __device__ static WGeom make(int n, int m, int T)
     {
         WGeom g;
@@ -105,99 +131,181 @@ struct WGeom {
         g.RT = n / 8 + 1;
         g.KS = g.NPOT / 4;
         g.LD = ld_of(g.NPOT);
-        g.BLK = ((g.NPOT + 1) * g.LD + 1) & ~1;
-        g.WSZ = g.NPOT * (g.NPOT + 2) + 32;
-        if (g.WSZ < 64) g.WSZ = 64;
+        g.BLK = ((n + 1) * g.LD + 1) & ~1;
         g.MT8 = (m + 7) / 8;
         g.mpad = 8 * g.MT8;
         g.MK = g.mpad / 4;
         g.npad = 8 * g.CT;
         g.LDB = (g.mpad % 8 == 4) ? g.mpad : g.mpad + 4;
         g.NTT = (T + 7) / 8;
-        g.NN = (n * n + 1) & ~1;
-        //          B            A1, A2 (+ overrun pad)   umax umin r2 rl     q2 q2f ql qfl qi qif
-        g.const_doubles = (size_t)n * g.LDB + 2 * ((size_t)n * g.LD + 8) + 4 * (size_t)g.mpad + 6 * (size_t)g.npad;
+        g.TP8 = 8 * g.NTT;
+        g.NN = g.NPOT * g.NPOT;
+        g.WB = 2 * g.mpad;
+        if (g.WB < 128) g.WB = 128;                    // also holds the 4 x 32 vectors of the backward sweep
+        //          B            A1, A2                umax umin r2 rl     q2 q2f ql qfl qi qif
+        g.const_doubles = (size_t)n * g.LDB + 2 * ((size_t)n * g.LD) + 4 * (size_t)g.mpad + 6 * (size_t)g.npad;
         g.const_doubles = (g.const_doubles + 1) & ~(size_t)1;
-        size_t wb = 2 * (size_t)g.mpad;
-        if (wb < 128) wb = 128;                        // also holds the 4 x 32 vectors of the backward sweep
-        g.warp_doubles = 3 * (size_t)g.BLK + (size_t)g.WSZ + wb;
+        g.warp_doubles = 3 * (size_t)g.BLK + (size_t)g.WB;
+        if (g.warp_doubles < 3 * (size_t)g.NN + 128) g.warp_doubles = 3 * (size_t)g.NN + 128;   // backward ring: 3 slots of NN + vectors
+        g.tail_doubles = 8 * (size_t)g.LDB + 16 * (size_t)g.LD + 8;   // overrun reads of the last rows stay inside the allocation
         return g;
     }
+    __host__ __device__ size_t smem_doubles(int warps) const { return const_doubles + (size_t)warps * warp_doubles + tail_doubles; }
 };
 
-// per-warp global scratch (doubles)
+// per-warp global scratch (doubles); u- and x-space arrays have TP8 = 8 ceil(T/8) rows so that the 8-row tiles
+// of the horizon GEMMs never need a row predicate (rows >= T hold zeros / finite junk that is never used)
 struct WsW {
-    size_t UC, UT, HU, HDU, DU, WV, DB, RDU;       // T x mpad
-    size_t XC, XT, HX, HDX, DX, RDX;               // T x npad
-    size_t RP, RPT, YV, DNU, BV;                   // (T+1) x npad
-    size_t Li, L1, L2;                             // (T+1) x NN
-    size_t total;
+    size_t tu, tx, tb, bl, total;
     __host__ __device__ static WsW make(const WGeom &g)
     {
         WsW L;
-        const size_t tu = (size_t)g.T * g.mpad, tx = (size_t)g.T * g.npad, tb = (size_t)(g.T + 1) * g.npad, bl = (size_t)(g.T + 1) * g.NN;
-        size_t o = 0;
-        L.UC = o; o += tu; L.UT = o; o += tu; L.HU = o; o += tu; L.HDU = o; o += tu; L.DU = o; o += tu; L.WV = o; o += tu;
-        L.DB = o; o += tu; L.RDU = o; o += tu;
-        L.XC = o; o += tx; L.XT = o; o += tx; L.HX = o; o += tx; L.HDX = o; o += tx; L.DX = o; o += tx; L.RDX = o; o += tx;
-        L.RP = o; o += tb; L.RPT = o; o += tb; L.YV = o; o += tb; L.DNU = o; o += tb; L.BV = o; o += tb;
-        L.Li = o; o += bl; L.L1 = o; o += bl; L.L2 = o; o += bl;
-        L.total = (o + 31) & ~(size_t)31;
+        L.tu = (size_t)g.TP8 * g.mpad;                 // UC UT HU HUT HDU DU WV DB RDU
+        L.tx = (size_t)g.TP8 * g.npad;                 // XC XT HX HXT HDX DX RDX
+        L.tb = (size_t)(g.TP8 + 1) * g.npad;           // RP RPT YV DNU BV
+        L.bl = (size_t)(g.T + 1) * g.NN;               // inv(L), L1, L2  (row-major, leading dimension NPOT)
+        L.total = (9 * L.tu + 7 * L.tx + 5 * L.tb + 3 * L.bl + 31) & ~(size_t)31;
         return L;
     }
 };
 
 struct WCtx {
     int n, m, T, NB, a2, has_xf;
-    int mpad, MK, MT8, npad, LDB, NTT, NN;
+    int mpad, MK, MT8, LDB, NTT;
     int lane, gq, q;
     double kappa;
-    // shared constants
-    const double *sB, *sA1, *sA2, *sUmax, *sUmin, *sR2, *sRl, *sQ2, *sQl, *sQi;   // sQ*: [2][npad] (0: stages < T, 1: stage T)
-    // per-warp shared
-    double *blk0, *blk1, *blk2, *bW, *wbuf;
-    // per-warp global scratch
-    double *UC, *UT, *HU, *HDU, *DU, *WV, *DB, *RDU, *XC, *XT, *HX, *HDX, *DX, *RDX, *RP, *RPT, *YV, *DNU, *BV, *gLi, *gL1, *gL2;
-    // pool of iterate-independent Schur blocks
+    // Everything below is addressed as base + index * stride, computed where it is used, so that a pass keeps
+    // only the few pointers it needs in registers.
+    double *smem;                       // CTA constants: B | A1 | A2 | umax umin r2 rl | q2[2] ql[2] qi[2]
+    int oA1, oA2, oU, oQ, npad;
+    double *wsm;                        // this warp's shared memory: 3 history blocks | w rows
+    int BLK;
+    double *ws;                         // this warp's global scratch (layout WsW)
+    int tu, tx, tb, bl;
+    int pp;                             // ping-pong parity of the iterate buffers
     const double *ypool;
     const int *ydi, *y1i, *y2i;
+    // start of the iterate (K_RP pass): warm start arrays of this instance or NULL = midpoint cold start
+    const double *U0, *X0, *xmin, *xmax;
+
+    __device__ __forceinline__ const double *sB() const { return smem; }
+    __device__ __forceinline__ const double *sA1() const { return smem + oA1; }
+    __device__ __forceinline__ const double *sA2() const { return smem + oA2; }
+    __device__ __forceinline__ const double *sUmax() const { return smem + oU; }
+    __device__ __forceinline__ const double *sUmin() const { return smem + oU + mpad; }
+    __device__ __forceinline__ const double *sR2() const { return smem + oU + 2 * mpad; }
+    __device__ __forceinline__ const double *sRl() const { return smem + oU + 3 * mpad; }
+    __device__ __forceinline__ const double *sQ2() const { return smem + oQ; }
+    __device__ __forceinline__ const double *sQl() const { return smem + oQ + 2 * npad; }
+    __device__ __forceinline__ const double *sQi() const { return smem + oQ + 4 * npad; }
+    __device__ __forceinline__ double *blk(int k) const { return wsm + k * BLK; }
+    __device__ __forceinline__ double *wbuf() const { return wsm + 3 * BLK; }
+    __device__ __forceinline__ double *ua(int a) const { return ws + (size_t)a * tu; }
+    __device__ __forceinline__ double *xa(int a) const { return ws + (size_t)9 * tu + (size_t)a * tx; }
+    __device__ __forceinline__ double *ba(int a) const { return ws + (size_t)9 * tu + (size_t)7 * tx + (size_t)a * tb; }
+    __device__ __forceinline__ double *fa(int a) const { return ws + (size_t)9 * tu + (size_t)7 * tx + (size_t)5 * tb + (size_t)a * bl; }
+    __device__ __forceinline__ double *UC() const { return ua(pp); }
+    __device__ __forceinline__ double *UT() const { return ua(pp ^ 1); }
+    __device__ __forceinline__ double *HU() const { return ua(2 + pp); }
+    __device__ __forceinline__ double *HUT() const { return ua(2 + (pp ^ 1)); }
+    __device__ __forceinline__ double *HDU() const { return ua(4); }
+    __device__ __forceinline__ double *DU() const { return ua(5); }
+    __device__ __forceinline__ double *WV() const { return ua(6); }
+    __device__ __forceinline__ double *DB() const { return ua(7); }
+    __device__ __forceinline__ double *RDU() const { return ua(8); }
+    __device__ __forceinline__ double *XC() const { return xa(pp); }
+    __device__ __forceinline__ double *XT() const { return xa(pp ^ 1); }
+    __device__ __forceinline__ double *HX() const { return xa(2 + pp); }
+    __device__ __forceinline__ double *HXT() const { return xa(2 + (pp ^ 1)); }
+    __device__ __forceinline__ double *HDX() const { return xa(4); }
+    __device__ __forceinline__ double *DX() const { return xa(5); }
+    __device__ __forceinline__ double *RDX() const { return xa(6); }
+    __device__ __forceinline__ double *RP() const { return ba(pp); }
+    __device__ __forceinline__ double *RPT() const { return ba(pp ^ 1); }
+    __device__ __forceinline__ double *YV() const { return ba(2); }
+    __device__ __forceinline__ double *DNU() const { return ba(3); }
+    __device__ __forceinline__ double *BV() const { return ba(4); }
+    __device__ __forceinline__ double *gLi() const { return fa(0); }
+    __device__ __forceinline__ double *gL1() const { return fa(1); }
+    __device__ __forceinline__ double *gL2() const { return fa(2); }
 };
 
 enum { K_RP = 0, K_NEWTON = 1, K_TRIAL = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // Horizon GEMM  acc[t][k] = (B v_u,t + A1 v_x,t-1 + A2 v_x,t-2)[k]  and its three uses
-//   K_RP     : v = z              ; RP  = x_t+1 - acc - b                     (r_p = C z - b, inf_newton_solver.m:14)
+//   K_RP     : v = z0 (start)     ; UC, XC <- z0 ; RP  = x_t+1 - acc - b      (fast_mpc_init.m:12-26, r_p = C z - b)
 //   K_NEWTON : v = inv(Phi) r_d   ; YV  = r_p - C v ; barrier terms, r_d, norms (inf_newton_KKT_H.m:3-13, :12, :28-29)
-//   K_TRIAL  : v = z + ts dz      ; RPT = C v - b ; r_d(ts) with d frozen, norms (backtracking_inf_newton.m:4)
+//   K_TRIAL  : v = z + ts dz      ; RPT = C v - b ; r_d(ts) with d frozen, norms (backtracking_inf_newton.m:4);
+//              the dual images at the trial point go to HUT / HXT so that accepting the step is a pointer swap
 // ss_d / ss_p return this lane's partial sums of squares (same accumulation order in NEWTON and TRIAL).
+// Every global stream is software pipelined: the loads of step k+1 are issued before the arithmetic and the
+// stores of step k (the scratch pointers may alias as far as the compiler knows, so it cannot do this itself).
 // ---------------------------------------------------------------------------------------------
+template <int KIND> struct UArr { static constexpr int N = (KIND == K_RP) ? 1 : (KIND == K_NEWTON ? 2 : 5); };
+
 template <int NPOT, int KIND>
 __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &ss_d, double &ss_p)
 {
-    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4;
-    const int n = c.n, T = c.T, mpad = c.mpad, npad = c.npad, gq = c.gq, q = c.q, lane = c.lane;
+    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, NA = UArr<KIND>::N, npad = 8 * CT;
+    constexpr int XU = 4;
+    const int n = c.n, m = c.m, T = c.T, mpad = c.mpad, gq = c.gq, q = c.q, lane = c.lane;
     ss_d = 0.0; ss_p = 0.0;
-    // ---- x-space elementwise (linear ownership), then visible to the whole warp ----
-    if (KIND == K_NEWTON) {
-        for (int e = lane; e < T * npad; e += 32) {
-            const int t = e / npad, k = e - t * npad, st = (t == T - 1) ? npad : 0;
-            const double r = rdx_expr(c.sQ2[st + k], c.sQl[st + k], c.XC[e], c.HX[e]);
-            c.RDX[e] = r;
-            ss_d = fma(r, r, ss_d);
-            c.DX[e] = r * c.sQi[st + k];                                   // p_x = inv(2Q) r_dx
-        }
-    } else if (KIND == K_TRIAL) {
-        for (int e = lane; e < T * npad; e += 32) {
-            const int t = e / npad, k = e - t * npad, st = (t == T - 1) ? npad : 0;
-            const double xv = __fma_rn(ts, c.DX[e], c.XC[e]);
-            c.XT[e] = xv;
-            const double r = rdx_expr(c.sQ2[st + k], c.sQl[st + k], xv, __fma_rn(ts, c.HDX[e], c.HX[e]));
-            ss_d = fma(r, r, ss_d);
+    // ---- x-space elementwise (linear ownership, XU elements in flight per lane), then visible to the whole warp ----
+    {
+        const int tot = T * npad;
+        double *pXC = c.XC(), *pHX = c.HX();
+        for (int e0 = lane; e0 < tot; e0 += 32 * XU) {
+            double a[XU], b[XU], d[XU], h[XU];
+#pragma unroll
+            for (int u = 0; u < XU; ++u) {
+                const int e = e0 + 32 * u;
+                a[u] = b[u] = d[u] = h[u] = 0.0;
+                if (e < tot) {
+                    if (KIND == K_RP) {
+                        const int t = e / npad, k = e - t * npad;
+                        if (k < n) a[u] = c.X0 ? c.X0[(size_t)t * n + k] : (c.xmin[k] + c.xmax[k]) / 2;
+                    } else if (KIND == K_NEWTON) {
+                        a[u] = pXC[e]; b[u] = pHX[e];
+                    } else {
+                        a[u] = pXC[e]; b[u] = pHX[e]; d[u] = c.DX()[e]; h[u] = c.HDX()[e];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < XU; ++u) {
+                const int e = e0 + 32 * u;
+                if (e < tot) {
+                    const int t = e / npad, k = e - t * npad, st = (t == T - 1) ? npad : 0;
+                    if (KIND == K_RP) {
+                        pXC[e] = a[u];
+                    } else if (KIND == K_NEWTON) {
+                        const double r = rdx_expr(c.sQ2()[st + k], c.sQl()[st + k], a[u], b[u]);
+                        c.RDX()[e] = r;
+                        ss_d = fma(r, r, ss_d);
+                        c.DX()[e] = r * c.sQi()[st + k];                        // p_x = inv(2Q) r_dx
+                    } else {
+                        const double xv = __fma_rn(ts, d[u], a[u]);
+                        const double hv = __fma_rn(ts, h[u], b[u]);
+                        c.XT()[e] = xv;
+                        c.HXT()[e] = hv;
+                        const double r = rdx_expr(c.sQ2()[st + k], c.sQl()[st + k], xv, hv);
+                        ss_d = fma(r, r, ss_d);
+                    }
+                }
+            }
         }
     }
     __syncwarp();
-    const double *xsrc = (KIND == K_RP) ? c.XC : (KIND == K_NEWTON ? c.DX : c.XT);
+    const double *xsrc = (KIND == K_RP) ? c.XC() : (KIND == K_NEWTON ? c.DX() : c.XT());
+    // operand row pointers (no predicates: see the conventions above WGeom)
+    const double *pB[CT];
+#pragma unroll
+    for (int nt = 0; nt < CT; ++nt) pB[nt] = c.sB() + (size_t)(8 * nt + gq) * c.LDB + q;
+    const double *pA1 = c.sA1() + gq * LD + q, *pA2 = c.sA2() + gq * LD + q;
+    const double *pUmax = c.sUmax() + q, *pUmin = c.sUmin() + q, *pR2 = c.sR2() + q, *pRl = c.sRl() + q;
+    // columns k >= n of the outputs must be stored as exact zeros (they pad the k index of later products)
+    const bool kok0 = (8 * (CT - 1) + 2 * q) < n, kok1 = (8 * (CT - 1) + 2 * q + 1) < n;
 
     for (int tt0 = 0; tt0 < c.NTT; tt0 += TTMAX) {
         const int TT = min(TTMAX, c.NTT - tt0);
@@ -206,103 +314,164 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
         for (int tt = 0; tt < TTMAX; ++tt)
 #pragma unroll
             for (int nt = 0; nt < CT; ++nt) acc[tt][nt][0] = acc[tt][nt][1] = 0.0;
-        // ---- u part: A fragment element (t = 8 tt + gq, j = 4 kk + q) is produced by its owner ----
-#pragma unroll 2
-        for (int kk = 0; kk < c.MK; ++kk) {
-            const int j = 4 * kk + q;
-            double a[TTMAX];
-#pragma unroll
-            for (int tt = 0; tt < TTMAX; ++tt) {
-                const int t = 8 * (tt0 + tt) + gq;
-                a[tt] = 0.0;
-                if (t < T) {
-                    const size_t idx = (size_t)t * mpad + j;
-                    if (KIND == K_RP) {
-                        a[tt] = c.UC[idx];
-                    } else if (KIND == K_NEWTON) {
-                        const double uu = c.UC[idx], h = c.HU[idx];
-                        const double sp = c.sUmax[j] - uu, sm = uu - c.sUmin[j];
-                        const double dp = rcp_nr(sp), dm = rcp_nr(sm);
-                        const double db = c.kappa * (dp - dm);
-                        const double r2 = c.sR2[j];
-                        const double w = rcp_nr(fma(c.kappa, fma(dp, dp, dm * dm), r2));
-                        const double r = rdu_expr(r2, c.sRl[j], uu, h, db);
-                        c.DB[idx] = db; c.WV[idx] = w; c.RDU[idx] = r;
-                        ss_d = fma(r, r, ss_d);
-                        a[tt] = r * w;                                      // p_u = inv(Phi_u) r_du
-                    } else {
-                        const double uv = __fma_rn(ts, c.DU[idx], c.UC[idx]);
-                        c.UT[idx] = uv;
-                        const double r = rdu_expr(c.sR2[j], c.sRl[j], uv, __fma_rn(ts, c.HDU[idx], c.HU[idx]), c.DB[idx]);
-                        ss_d = fma(r, r, ss_d);
-                        a[tt] = uv;
-                    }
-                }
-            }
-            double bf[CT];
-#pragma unroll
-            for (int nt = 0; nt < CT; ++nt) bf[nt] = ldp(c.sB + (size_t)(8 * nt + gq) * c.LDB + j, 8 * nt + gq < n);
-#pragma unroll
-            for (int tt = 0; tt < TTMAX; ++tt)
-                if (tt < TT) {
-#pragma unroll
-                    for (int nt = 0; nt < CT; ++nt) dmma(acc[tt][nt], a[tt], bf[nt]);
-                }
-        }
-        // ---- x part: A1 v_{t-1} + A2 v_{t-2} (shifted rows read from the scratch arrays) ----
-#pragma unroll
-        for (int kk = 0; kk < KS; ++kk) {
-            const int kc = 4 * kk + q;
-            double a1[TTMAX], a2[TTMAX];
-#pragma unroll
-            for (int tt = 0; tt < TTMAX; ++tt) {
-                const int t = 8 * (tt0 + tt) + gq;
-                a1[tt] = (t < T && t >= 1 && kc < n) ? xsrc[(size_t)(t - 1) * npad + kc] : 0.0;
-                a2[tt] = (c.a2 && t < T && t >= 2 && kc < n) ? xsrc[(size_t)(t - 2) * npad + kc] : 0.0;
-            }
-            double b1[CT], b2[CT];
-#pragma unroll
-            for (int nt = 0; nt < CT; ++nt) {
-                const bool ok = (8 * nt + gq < n) && (kc < n);
-                b1[nt] = ldp(c.sA1 + (size_t)(8 * nt + gq) * LD + kc, ok);
-                b2[nt] = ldp(c.sA2 + (size_t)(8 * nt + gq) * LD + kc, ok && c.a2);
-            }
-#pragma unroll
-            for (int tt = 0; tt < TTMAX; ++tt)
-                if (tt < TT) {
-#pragma unroll
-                    for (int nt = 0; nt < CT; ++nt) {
-                        dmma(acc[tt][nt], a1[tt], b1[nt]);
-                        if (c.a2) dmma(acc[tt][nt], a2[tt], b2[nt]);
-                    }
-                }
-        }
-        // ---- epilogue in the accumulator layout: (t = 8 tt + gq, k = 8 nt + 2 q + e) ----
+        int row[TTMAX];                                      // element offset of (t, q) in a u-space array
+        bool tok[TTMAX];
 #pragma unroll
         for (int tt = 0; tt < TTMAX; ++tt) {
             const int t = 8 * (tt0 + tt) + gq;
-            if (tt < TT && t < T) {
+            tok[tt] = (tt < TT) && (t < T);
+            row[tt] = ((tt < TT) ? t : 0) * mpad + q;        // rows of dead tiles alias row 0 (finite data, unused result)
+        }
+        // ---- u part: A fragment element (t = 8 tt + gq, j = 4 kk + q) is produced by its owner; kk in pairs ----
+        double cur[2][TTMAX][NA], nxt[2][TTMAX][NA];
+        auto load = [&](double (&bf)[2][TTMAX][NA], const int kp) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j4 = 8 * kp + 4 * h;
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt) {
+                    const int idx = row[tt] + j4;
+                    if (KIND == K_RP) {
+                        const int t = 8 * (tt0 + tt) + gq, j = j4 + q;
+                        bf[h][tt][0] = (tok[tt] && j < m) ? (c.U0 ? c.U0[(size_t)t * m + j] : (pUmin[j4] + pUmax[j4]) / 2) : 0.0;
+                    } else if (KIND == K_NEWTON) {
+                        bf[h][tt][0] = c.UC()[idx]; bf[h][tt][NA > 1 ? 1 : 0] = c.HU()[idx];
+                    } else {
+                        bf[h][tt][0] = c.UC()[idx]; bf[h][tt][NA > 1 ? 1 : 0] = c.DU()[idx]; bf[h][tt][NA > 2 ? 2 : 0] = c.HU()[idx];
+                        bf[h][tt][NA > 3 ? 3 : 0] = c.HDU()[idx]; bf[h][tt][NA > 4 ? 4 : 0] = c.DB()[idx];
+                    }
+                }
+            }
+        };
+        const int NKP = c.MK / 2;
+        load(cur, 0);
+        for (int kp = 0; kp < NKP; ++kp) {
+            if (kp + 1 < NKP) load(nxt, kp + 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j4 = 8 * kp + 4 * h;
+                double a[TTMAX];
+                double bf[CT];
+#pragma unroll
+                for (int nt = 0; nt < CT; ++nt) bf[nt] = pB[nt][j4];
+                const double r2 = pR2[j4], rl = pRl[j4];
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt) {
+                    const int idx = row[tt] + j4;
+                    if (KIND == K_RP) {
+                        a[tt] = cur[h][tt][0];
+                        if (tt < TT) c.UC()[idx] = a[tt];
+                    } else if (KIND == K_NEWTON) {
+                        const double uu = cur[h][tt][0], hh = cur[h][tt][NA > 1 ? 1 : 0];
+                        const double sp = pUmax[j4] - uu, sm = uu - pUmin[j4];
+                        const double dp = rcp_nr(sp), dm = rcp_nr(sm);
+                        const double db = c.kappa * (dp - dm);
+                        const double w = rcp_nr(fma(c.kappa, fma(dp, dp, dm * dm), r2));
+                        const double r = rdu_expr(r2, rl, uu, hh, db);
+                        if (tt < TT) { c.DB()[idx] = db; c.WV()[idx] = w; c.RDU()[idx] = r; }
+                        const double rm = tok[tt] ? r : 0.0;
+                        ss_d = fma(rm, rm, ss_d);
+                        a[tt] = r * w;                                      // p_u = inv(Phi_u) r_du
+                    } else {
+                        const double uv = __fma_rn(ts, cur[h][tt][NA > 1 ? 1 : 0], cur[h][tt][0]);
+                        const double hv = __fma_rn(ts, cur[h][tt][NA > 3 ? 3 : 0], cur[h][tt][NA > 2 ? 2 : 0]);
+                        if (tt < TT) { c.UT()[idx] = uv; c.HUT()[idx] = hv; }
+                        const double r = rdu_expr(r2, rl, uv, hv, cur[h][tt][NA > 4 ? 4 : 0]);
+                        const double rm = tok[tt] ? r : 0.0;
+                        ss_d = fma(rm, rm, ss_d);
+                        a[tt] = uv;
+                    }
+                }
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt)
+                    if (tt < TT) {
+#pragma unroll
+                        for (int nt = 0; nt < CT; ++nt) dmma(acc[tt][nt], a[tt], bf[nt]);
+                    }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt)
+#pragma unroll
+                    for (int a = 0; a < NA; ++a) cur[h][tt][a] = nxt[h][tt][a];
+        }
+        // ---- x part: A1 v_{t-1} + A2 v_{t-2} (shifted rows read from the scratch arrays, all loads up front) ----
+        {
+            double a1[KS][TTMAX], a2[KS][TTMAX];
+#pragma unroll
+            for (int tt = 0; tt < TTMAX; ++tt) {
+                const int t = 8 * (tt0 + tt) + gq;
+                const bool ok1 = tok[tt] && t >= 1, ok2 = tok[tt] && t >= 2;
+                const double *p1 = xsrc + (size_t)(ok1 ? t - 1 : 0) * npad + q, *p2 = xsrc + (size_t)(ok2 ? t - 2 : 0) * npad + q;
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const double v1 = p1[4 * kk], v2 = p2[4 * kk];   // columns >= n of the scratch arrays are zero
+                    a1[kk][tt] = ok1 ? v1 : 0.0;
+                    a2[kk][tt] = ok2 ? v2 : 0.0;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                double b1[CT], b2[CT];
+#pragma unroll
+                for (int nt = 0; nt < CT; ++nt) { b1[nt] = pA1[8 * nt * LD + 4 * kk]; b2[nt] = pA2[8 * nt * LD + 4 * kk]; }
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt)
+                    if (tt < TT) {
+#pragma unroll
+                        for (int nt = 0; nt < CT; ++nt) {
+                            dmma(acc[tt][nt], a1[kk][tt], b1[nt]);
+                            dmma(acc[tt][nt], a2[kk][tt], b2[nt]);          // A2 = 0 for a VAR(1) model
+                        }
+                    }
+            }
+        }
+        // ---- epilogue in the accumulator layout: (t = 8 tt + gq, k = 8 nt + 2 q + e); loads first ----
+        {
+            double2 e1[TTMAX][CT], e2[TTMAX][CT];
+#pragma unroll
+            for (int tt = 0; tt < TTMAX; ++tt) {
+                const int t = 8 * (tt0 + tt) + gq;
 #pragma unroll
                 for (int nt = 0; nt < CT; ++nt) {
-                    const size_t idx = (size_t)t * npad + 8 * nt + 2 * q;
-                    if (KIND == K_RP || KIND == K_TRIAL) {
-                        const double2 xv = *reinterpret_cast<const double2 *>(xsrc + idx);
-                        const double2 bb = *reinterpret_cast<const double2 *>(c.BV + idx);
-                        double2 r;
-                        r.x = xv.x - acc[tt][nt][0] - bb.x;
-                        r.y = xv.y - acc[tt][nt][1] - bb.y;
-                        *reinterpret_cast<double2 *>((KIND == K_RP ? c.RP : c.RPT) + idx) = r;
-                        ss_p = fma(r.x, r.x, ss_p);
-                        ss_p = fma(r.y, r.y, ss_p);
-                    } else {
-                        const double2 rp = *reinterpret_cast<const double2 *>(c.RP + idx);
-                        const double2 px = *reinterpret_cast<const double2 *>(c.DX + idx);
-                        ss_p = fma(rp.x, rp.x, ss_p);
-                        ss_p = fma(rp.y, rp.y, ss_p);
-                        double2 y;
-                        y.x = rp.x - px.x + acc[tt][nt][0];                  // -beta = r_p - C p
-                        y.y = rp.y - px.y + acc[tt][nt][1];
-                        *reinterpret_cast<double2 *>(c.YV + idx) = y;
+                    e1[tt][nt] = e2[tt][nt] = make_double2(0.0, 0.0);
+                    if (tok[tt]) {
+                        const size_t idx = (size_t)t * npad + 8 * nt + 2 * q;
+                        if (KIND == K_RP || KIND == K_TRIAL) {
+                            e1[tt][nt] = *reinterpret_cast<const double2 *>(xsrc + idx);
+                            e2[tt][nt] = *reinterpret_cast<const double2 *>(c.BV() + idx);
+                        } else {
+                            e1[tt][nt] = *reinterpret_cast<const double2 *>(c.RP() + idx);
+                            e2[tt][nt] = *reinterpret_cast<const double2 *>(c.DX() + idx);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int tt = 0; tt < TTMAX; ++tt) {
+                const int t = 8 * (tt0 + tt) + gq;
+                if (tok[tt]) {
+#pragma unroll
+                    for (int nt = 0; nt < CT; ++nt) {
+                        const size_t idx = (size_t)t * npad + 8 * nt + 2 * q;
+                        const bool k0 = (nt < CT - 1) || kok0, k1 = (nt < CT - 1) || kok1;
+                        if (KIND == K_RP || KIND == K_TRIAL) {
+                            double2 r;
+                            r.x = k0 ? e1[tt][nt].x - acc[tt][nt][0] - e2[tt][nt].x : 0.0;
+                            r.y = k1 ? e1[tt][nt].y - acc[tt][nt][1] - e2[tt][nt].y : 0.0;
+                            *reinterpret_cast<double2 *>((KIND == K_RP ? c.RP() : c.RPT()) + idx) = r;
+                            ss_p = fma(r.x, r.x, ss_p);
+                            ss_p = fma(r.y, r.y, ss_p);
+                        } else {
+                            const double2 rp = e1[tt][nt], px = e2[tt][nt];
+                            ss_p = fma(rp.x, rp.x, ss_p);
+                            ss_p = fma(rp.y, rp.y, ss_p);
+                            double2 y;
+                            y.x = k0 ? rp.x - px.x + acc[tt][nt][0] : 0.0;   // -beta = r_p - C p
+                            y.y = k1 ? rp.y - px.y + acc[tt][nt][1] : 0.0;
+                            *reinterpret_cast<double2 *>(c.YV() + idx) = y;
+                        }
                     }
                 }
             }
@@ -312,45 +481,70 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
     if (c.has_xf && lane < n) {
         const size_t iT = (size_t)T * npad + lane, iL = (size_t)(T - 1) * npad + lane;
         if (KIND == K_RP || KIND == K_TRIAL) {
-            const double r = xsrc[iL] - c.BV[iT];
-            (KIND == K_RP ? c.RP : c.RPT)[iT] = r;
+            const double r = xsrc[iL] - c.BV()[iT];
+            (KIND == K_RP ? c.RP() : c.RPT())[iT] = r;
             ss_p = fma(r, r, ss_p);
         } else {
-            const double rp = c.RP[iT];
+            const double rp = c.RP()[iT];
             ss_p = fma(rp, rp, ss_p);
-            c.YV[iT] = rp - c.DX[iL];
+            c.YV()[iT] = rp - c.DX()[iL];
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// C' v for v = V (rows t < NB, leading dimension ldv):  hu_t = B' v_t ,  hx_t = v_t - A1' v_{t+1} - A2' v_{t+2} (+ v_T)
+// C' v for v = V = DNU buffer (rows t < NB, leading dimension npad, columns >= n zero):
+//   hu_t = B' v_t ,  hx_t = v_t - A1' v_{t+1} - A2' v_{t+2} (+ v_T)
 //   MODE 0 : HU, HX stored (images of the dual start)
 //   MODE 1 : HDU, HDX stored and  du = -(r_du - hdu) w ,  dx = -(r_dx + hdx) inv(2Q)      (inf_newton_solver.m:34-35)
 // ---------------------------------------------------------------------------------------------
 template <int NPOT, int MODE>
-__device__ __forceinline__ void pass_Ct(const WCtx &c, const double *V, const int ldv)
+__device__ __forceinline__ void pass_Ct(const WCtx &c)
 {
-    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4;
-    const int n = c.n, T = c.T, mpad = c.mpad, npad = c.npad, gq = c.gq, q = c.q;
+    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, npad = 8 * CT;
+    const int n = c.n, T = c.T, mpad = c.mpad, gq = c.gq, q = c.q;
+    const double *V = c.DNU();
+    const double *pBk[KS];                                   // B rows k = 4 kk + q, column gq
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) pBk[kk] = c.sB() + (size_t)(4 * kk + q) * c.LDB + gq;
+    const double *pA1 = c.sA1() + q * LD + gq, *pA2 = c.sA2() + q * LD + gq;
+    const bool kok0 = (8 * (CT - 1) + 2 * q) < n, kok1 = (8 * (CT - 1) + 2 * q + 1) < n;
     for (int tt0 = 0; tt0 < c.NTT; tt0 += TTMAX) {
         const int TT = min(TTMAX, c.NTT - tt0);
+        bool tok[TTMAX];
+#pragma unroll
+        for (int tt = 0; tt < TTMAX; ++tt) tok[tt] = (tt < TT) && (8 * (tt0 + tt) + gq < T);
         {   // ---- u part ----
             double av[TTMAX][KS];
 #pragma unroll
-            for (int tt = 0; tt < TTMAX; ++tt)
+            for (int tt = 0; tt < TTMAX; ++tt) {
+                const int t = 8 * (tt0 + tt) + gq;
+                const double *pv = V + (size_t)(tok[tt] ? t : 0) * npad + q;
 #pragma unroll
-                for (int kk = 0; kk < KS; ++kk) {
-                    const int t = 8 * (tt0 + tt) + gq, kc = 4 * kk + q;
-                    av[tt][kk] = (t < T && kc < n) ? V[(size_t)t * ldv + kc] : 0.0;
+                for (int kk = 0; kk < KS; ++kk) { const double v = pv[4 * kk]; av[tt][kk] = tok[tt] ? v : 0.0; }
+            }
+            double2 rc[TTMAX], wc[TTMAX], rn[TTMAX], wn[TTMAX];
+            auto loadrw = [&](double2 (&r)[TTMAX], double2 (&w)[TTMAX], const int jt) {
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt) {
+                    const int t = 8 * (tt0 + tt) + gq;
+                    r[tt] = w[tt] = make_double2(0.0, 0.0);
+                    if (MODE == 1 && tok[tt]) {
+                        const size_t idx = (size_t)t * mpad + 8 * jt + 2 * q;
+                        r[tt] = *reinterpret_cast<const double2 *>(c.RDU() + idx);
+                        w[tt] = *reinterpret_cast<const double2 *>(c.WV() + idx);
+                    }
                 }
+            };
+            loadrw(rc, wc, 0);
             for (int jt = 0; jt < c.MT8; ++jt) {
+                if (jt + 1 < c.MT8) loadrw(rn, wn, jt + 1);
                 double acc[TTMAX][2];
 #pragma unroll
                 for (int tt = 0; tt < TTMAX; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
 #pragma unroll
                 for (int kk = 0; kk < KS; ++kk) {
-                    const double bf = ldp(c.sB + (size_t)(4 * kk + q) * c.LDB + 8 * jt + gq, 4 * kk + q < n);
+                    const double bf = pBk[kk][8 * jt];               // rows k >= n meet av = 0
 #pragma unroll
                     for (int tt = 0; tt < TTMAX; ++tt)
                         if (tt < TT) dmma(acc[tt], av[tt][kk], bf);
@@ -358,25 +552,39 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c, const double *V, const in
 #pragma unroll
                 for (int tt = 0; tt < TTMAX; ++tt) {
                     const int t = 8 * (tt0 + tt) + gq;
-                    if (tt < TT && t < T) {
+                    if (tok[tt]) {
                         const size_t idx = (size_t)t * mpad + 8 * jt + 2 * q;
                         const double2 h = make_double2(acc[tt][0], acc[tt][1]);
                         if (MODE == 0) {
-                            *reinterpret_cast<double2 *>(c.HU + idx) = h;
+                            *reinterpret_cast<double2 *>(c.HU() + idx) = h;
                         } else {
-                            *reinterpret_cast<double2 *>(c.HDU + idx) = h;
-                            const double2 r = *reinterpret_cast<const double2 *>(c.RDU + idx);
-                            const double2 w = *reinterpret_cast<const double2 *>(c.WV + idx);
+                            *reinterpret_cast<double2 *>(c.HDU() + idx) = h;
                             double2 d;
-                            d.x = -(r.x - h.x) * w.x;
-                            d.y = -(r.y - h.y) * w.y;
-                            *reinterpret_cast<double2 *>(c.DU + idx) = d;
+                            d.x = -(rc[tt].x - h.x) * wc[tt].x;
+                            d.y = -(rc[tt].y - h.y) * wc[tt].y;
+                            *reinterpret_cast<double2 *>(c.DU() + idx) = d;
                         }
                     }
                 }
+#pragma unroll
+                for (int tt = 0; tt < TTMAX; ++tt) { rc[tt] = rn[tt]; wc[tt] = wn[tt]; }
             }
         }
-        {   // ---- x part ----
+        {   // ---- x part (global loads up front; the epilogue operands two k-steps before the end) ----
+            double a1[KS][TTMAX], a2[KS][TTMAX];
+#pragma unroll
+            for (int tt = 0; tt < TTMAX; ++tt) {
+                const int t = 8 * (tt0 + tt) + gq;
+                const bool ok1 = (tt < TT) && (t + 1 < T), ok2 = (tt < TT) && (t + 2 < T);
+                const double *p1 = V + (size_t)(ok1 ? t + 1 : 0) * npad + q, *p2 = V + (size_t)(ok2 ? t + 2 : 0) * npad + q;
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const double v1 = p1[4 * kk], v2 = p2[4 * kk];
+                    a1[kk][tt] = ok1 ? v1 : 0.0;
+                    a2[kk][tt] = ok2 ? v2 : 0.0;
+                }
+            }
+            double2 vown[TTMAX][CT], vterm[CT], rdx[TTMAX][CT];
             double acc[TTMAX][CT][2];
 #pragma unroll
             for (int tt = 0; tt < TTMAX; ++tt)
@@ -384,58 +592,58 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c, const double *V, const in
                 for (int nt = 0; nt < CT; ++nt) acc[tt][nt][0] = acc[tt][nt][1] = 0.0;
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
-                const int kc = 4 * kk + q;
-                double a1[TTMAX], a2[TTMAX];
+                if (kk == (KS >= 2 ? KS - 2 : 0)) {
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt) {
-                    const int t = 8 * (tt0 + tt) + gq;
-                    a1[tt] = (t + 1 < T && kc < n) ? V[(size_t)(t + 1) * ldv + kc] : 0.0;
-                    a2[tt] = (c.a2 && t + 2 < T && kc < n) ? V[(size_t)(t + 2) * ldv + kc] : 0.0;
+                    for (int nt = 0; nt < CT; ++nt)
+                        vterm[nt] = c.has_xf ? *reinterpret_cast<const double2 *>(V + (size_t)T * npad + 8 * nt + 2 * q) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int tt = 0; tt < TTMAX; ++tt) {
+                        const int t = 8 * (tt0 + tt) + gq;
+#pragma unroll
+                        for (int nt = 0; nt < CT; ++nt) {
+                            vown[tt][nt] = rdx[tt][nt] = make_double2(0.0, 0.0);
+                            if (tok[tt]) {
+                                vown[tt][nt] = *reinterpret_cast<const double2 *>(V + (size_t)t * npad + 8 * nt + 2 * q);
+                                if (MODE == 1) rdx[tt][nt] = *reinterpret_cast<const double2 *>(c.RDX() + (size_t)t * npad + 8 * nt + 2 * q);
+                            }
+                        }
+                    }
                 }
                 double b1[CT], b2[CT];
 #pragma unroll
-                for (int nt = 0; nt < CT; ++nt) {
-                    const bool ok = (kc < n) && (8 * nt + gq < n);
-                    b1[nt] = ldp(c.sA1 + (size_t)kc * LD + 8 * nt + gq, ok);
-                    b2[nt] = ldp(c.sA2 + (size_t)kc * LD + 8 * nt + gq, ok && c.a2);
-                }
+                for (int nt = 0; nt < CT; ++nt) { b1[nt] = pA1[4 * kk * LD + 8 * nt]; b2[nt] = pA2[4 * kk * LD + 8 * nt]; }
 #pragma unroll
                 for (int tt = 0; tt < TTMAX; ++tt)
                     if (tt < TT) {
 #pragma unroll
                         for (int nt = 0; nt < CT; ++nt) {
-                            dmma(acc[tt][nt], a1[tt], b1[nt]);
-                            if (c.a2) dmma(acc[tt][nt], a2[tt], b2[nt]);
+                            dmma(acc[tt][nt], a1[kk][tt], b1[nt]);
+                            dmma(acc[tt][nt], a2[kk][tt], b2[nt]);
                         }
                     }
             }
 #pragma unroll
             for (int tt = 0; tt < TTMAX; ++tt) {
                 const int t = 8 * (tt0 + tt) + gq;
-                if (tt < TT && t < T) {
+                if (tok[tt]) {
                     const int st = (t == T - 1) ? npad : 0;
 #pragma unroll
                     for (int nt = 0; nt < CT; ++nt) {
                         const int k0 = 8 * nt + 2 * q;
-                        double h[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int k = k0 + e;
-                            double v = (k < n) ? V[(size_t)t * ldv + k] : 0.0;
-                            v -= acc[tt][nt][e];
-                            if (c.has_xf && t == T - 1 && k < n) v += V[(size_t)T * ldv + k];
-                            h[e] = v;
-                        }
+                        const bool ok0 = (nt < CT - 1) || kok0, ok1 = (nt < CT - 1) || kok1;
+                        double h0 = vown[tt][nt].x - acc[tt][nt][0], h1 = vown[tt][nt].y - acc[tt][nt][1];
+                        if (t == T - 1) { h0 += vterm[nt].x; h1 += vterm[nt].y; }
+                        h0 = ok0 ? h0 : 0.0;                                   // columns >= n stay exact zeros
+                        h1 = ok1 ? h1 : 0.0;
                         const size_t idx = (size_t)t * npad + k0;
                         if (MODE == 0) {
-                            *reinterpret_cast<double2 *>(c.HX + idx) = make_double2(h[0], h[1]);
+                            *reinterpret_cast<double2 *>(c.HX() + idx) = make_double2(h0, h1);
                         } else {
-                            *reinterpret_cast<double2 *>(c.HDX + idx) = make_double2(h[0], h[1]);
-                            const double2 r = *reinterpret_cast<const double2 *>(c.RDX + idx);
+                            *reinterpret_cast<double2 *>(c.HDX() + idx) = make_double2(h0, h1);
                             double2 d;
-                            d.x = -(r.x + h[0]) * c.sQi[st + k0];
-                            d.y = -(r.y + h[1]) * c.sQi[st + k0 + 1];
-                            *reinterpret_cast<double2 *>(c.DX + idx) = d;
+                            d.x = -(rdx[tt][nt].x + h0) * c.sQi()[st + k0];
+                            d.y = -(rdx[tt][nt].y + h1) * c.sQi()[st + k0 + 1];
+                            *reinterpret_cast<double2 *>(c.DX() + idx) = d;
                         }
                     }
                 }
@@ -445,87 +653,46 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c, const double *V, const in
 }
 
 // ---------------------------------------------------------------------------------------------
-// One warp: Cholesky of the n x n block held (lower triangle, leading dimension NP+1) in bW, and the
-// explicit inverse of the factor.  S = U D U' right-looking with row r in the registers of lane r
-// (pivot chain through shuffles), then V = inv(U) column j by lane j, inv(L) = diag(1/sqrt(d)) V.
-// Outputs: inv(L) in DMMA B-fragment order in bW (tile pair (ct, jt <= ct): 64 doubles, slot
-// 2 * (4 gq + q) + e  <->  inv(L)(8 ct + gq, 8 jt + 2 q + e)), and row-major n x n in gLinv.
-// Returns 0 or failing column + 1 (uniform).
+// 8 x 8 diagonal block in accumulator layout (thread (gq,q) holds D[gq][2q], D[gq][2q+1]): right-looking Cholesky
+// with the inverse of the factor formed alongside (forward elimination applied to the identity).  Only the first
+// nv columns are pivots; rows below them (e.g. the rhs row) are carried as ordinary rows.
+// On exit d = L (lower triangle; the rest is junk), x = inv(L) (lower triangular).  Returns 0 or failing column + 1.
 // ---------------------------------------------------------------------------------------------
-template <int NP>
-__device__ __forceinline__ int warp_potrf_inverse(double *bW, const int n, double *gLinv, const int lane)
+__device__ __forceinline__ int diag8(double (&d)[2], double (&x)[2], const int nv, const int gq, const int q)
 {
-    constexpr int LDS_ = NP + 1, LDU = NP + 2, CT = (NP + 7) / 8;
-    const int r = lane;
-    double a[NP];
-#pragma unroll
-    for (int cc = 0; cc < NP; ++cc) a[cc] = (r < n && cc < r) ? bW[r * LDS_ + cc] : 0.0;
-    double diag = (r < n) ? bW[r * LDS_ + r] : 1.0;
-    double dpiv = 1.0;
+    x[0] = (2 * q == gq) ? 1.0 : 0.0;
+    x[1] = (2 * q + 1 == gq) ? 1.0 : 0.0;
     int info = 0;
-    __syncwarp();                                           // S is in registers: bW is free
-    double *colbuf = bW;                                    // 2 x 32
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        const double d = __shfl_sync(FULL, diag, k);        // pivot of column k
-        if (!(d > 0.0) || !(d < 1.0e300)) { if (!info) info = k + 1; }
-        if (lane == k) dpiv = d;
-        const double at = a[k];
-        if (k + 1 < NP) {
-            double *cb = colbuf + (k & 1) * 32;
-            cb[lane] = at;
-            const double dinv = rcp_nr(d);
-            const double t = at * dinv;                     // U(r,k)
-            a[k] = t;
-            diag = fma(-t, at, diag);
-            __syncwarp();
-            if ((k + 1) & 1) a[k + 1] = fma(-t, cb[k + 1], a[k + 1]);
-#pragma unroll
-            for (int c2 = (k + 2) & ~1; c2 + 1 < NP; c2 += 2) {
-                const double2 p = *reinterpret_cast<const double2 *>(cb + c2);
-                a[c2] = fma(-t, p.x, a[c2]);
-                a[c2 + 1] = fma(-t, p.y, a[c2 + 1]);
-            }
+    for (int cidx = 0; cidx < 8; ++cidx) {
+        if (cidx < nv) {
+            const int qc = cidx >> 1, ec = cidx & 1;
+            const double p = shfl_d(d[ec], 4 * cidx + qc);              // pivot D[c][c]
+            if (!(p > 0.0) || !(p < 1.0e300)) { if (!info) info = cidx + 1; }
+            const double rs = rsqrt_nr(p);
+            const double mine = d[ec] * rs;                              // column c scaled (held where q == qc)
+            const double lr = shfl_d(mine, 4 * gq + qc);                 // L[gq][c]
+            const double lc0 = shfl_d(mine, 4 * (2 * q) + qc);           // L[2q][c]
+            const double lc1 = shfl_d(mine, 4 * (2 * q + 1) + qc);       // L[2q+1][c]
+            if (q == qc) d[ec] = lr;
+            if (2 * q > cidx) d[0] = fma(-lr, lc0, d[0]);
+            if (2 * q + 1 > cidx) d[1] = fma(-lr, lc1, d[1]);
+            const double e0 = shfl_d(x[0], 4 * cidx + q) * rs, e1 = shfl_d(x[1], 4 * cidx + q) * rs;
+            if (gq == cidx) { x[0] = e0; x[1] = e1; }
+            else if (gq > cidx) { x[0] = fma(-lr, e0, x[0]); x[1] = fma(-lr, e1, x[1]); }
         }
     }
-    if (info) return info;
-    __syncwarp();                                           // column buffer dead
-    double *bU = bW, *rsv = bW + NP * LDU;
-    rsv[lane] = rsqrt(dpiv);
-    if (r < NP) {
+    return info;
+}
+// transpose of an 8 x 8 tile in accumulator layout
+__device__ __forceinline__ void tile_T(double (&o)[2], const double (&t)[2], const int gq, const int q)
+{
 #pragma unroll
-        for (int cc = 0; cc + 1 < NP; cc += 2) *reinterpret_cast<double2 *>(bU + r * LDU + cc) = make_double2(a[cc], a[cc + 1]);
+    for (int e = 0; e < 2; ++e) {
+        const int src = 4 * (2 * q + e) + (gq >> 1);
+        const double v0 = shfl_d(t[0], src), v1 = shfl_d(t[1], src);
+        o[e] = (gq & 1) ? v1 : v0;
     }
-    __syncwarp();
-    const int j = lane;
-    double v[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-        for (int k = 0; k + 1 < i; k += 2) {
-            const double2 p = *reinterpret_cast<const double2 *>(bU + i * LDU + k);
-            s0 = fma(p.x, v[k], s0);
-            s1 = fma(p.y, v[k + 1], s1);
-        }
-        if (i & 1) s0 = fma(bU[i * LDU + i - 1], v[i - 1], s0);
-        v[i] = (i < j) ? 0.0 : ((i == j) ? 1.0 : -(s0 + s1));
-    }
-    double rs[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) rs[i] = rsv[i];
-    __syncwarp();                                           // U and rsv consumed: the fragment area may be written
-    const bool live = (j < n);
-    const int jt = j >> 3, jslot = 2 * ((j & 7) >> 1) + (j & 1);           // 2 q' + e
-#pragma unroll
-    for (int i = 0; i < 8 * CT; ++i) {
-        const int ct = i >> 3, gqp = i & 7;
-        double val = 0.0;
-        if (i < NP) val = (live && i < n) ? v[i < NP ? i : 0] * rs[i < NP ? i : 0] : 0.0;
-        if (j < 8 * CT && jt <= ct) bW[(ct * (ct + 1) / 2 + jt) * 64 + 8 * gqp + jslot] = val;
-        if (live && i < n) gLinv[i * n + j] = val;
-    }
-    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,17 +700,18 @@ __device__ __forceinline__ int warp_potrf_inverse(double *bW, const int n, doubl
 // On return YV holds y = inv(L) (-beta).  Returns 0 or the failing stage + 1.
 // ---------------------------------------------------------------------------------------------
 template <int NPOT, int RT>
-__device__ __forceinline__ int forward_sweep(const WCtx &c)
+__device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
 {
-    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, LDS_ = NPOT + 1;
-    const int n = c.n, T = c.T, NB = c.NB, mpad = c.mpad, npad = c.npad, gq = c.gq, q = c.q, lane = c.lane;
-    const int yr_gq = n & 7;                                // row n lives in tile RT-1, fragment row yr_gq
-    const bool yrow = (gq == yr_gq);
-    const size_t nn = (size_t)n * n;
-    double *bL1 = c.blk0, *bL2p = c.blk1, *bL2pp = c.blk2, *bW = c.bW;
+    constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, npad = 8 * CT;
+    const int n = c.n, T = c.T, NB = c.NB, mpad = c.mpad, gq = c.gq, q = c.q, lane = c.lane;
+    const bool yrow = (gq == (n & 7));                       // row n lives in tile RT-1, fragment row n % 8
+    const int nn = n * n;
+    double *bL1 = c.blk(0), *bL2p = c.blk(1), *bL2pp = c.blk(2);
+    const bool cok0 = (8 * (CT - 1) + 2 * q) < NPOT, cok1 = (8 * (CT - 1) + 2 * q + 1) < NPOT;     // block columns < NPOT
+    const bool nok0 = (8 * (CT - 1) + 2 * q) < n, nok1 = (8 * (CT - 1) + 2 * q + 1) < n;          // real columns < n
 
     // stage the first w row
-    for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf + 2 * ch, c.WV + 2 * ch);
+    for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf() + 2 * ch, c.WV() + 2 * ch);
     cp_async_commit();
 
     for (int i = 0; i < NB; ++i) {
@@ -555,24 +723,48 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c)
         for (int rt = 0; rt < RT; ++rt)
 #pragma unroll
             for (int ct = 0; ct < CT; ++ct) sacc[rt][ct][0] = sacc[rt][ct][1] = 0.0;
+        // iterate-independent part of Y[i,i] and -beta_i: requested now, consumed after the B diag(w) B' loop
+        double ydv[CT][CT][2];
+        double2 yrv[CT];
+        {
+            const int yd = c.ydi[i];
+            const double *Yd = c.ypool + (size_t)(yd >= 0 ? yd : 0) * nn;
+#pragma unroll
+            for (int rt = 0; rt < CT; ++rt) {
+                const int r = 8 * rt + gq;
+#pragma unroll
+                for (int ct = 0; ct <= rt; ++ct) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = 8 * ct + 2 * q + e;
+                        ydv[rt][ct][e] = (yd >= 0 && r < n && cc <= r) ? __ldg(Yd + r * n + cc) : 0.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int ct = 0; ct < CT; ++ct)
+                yrv[ct] = yrow ? *reinterpret_cast<const double2 *>(c.YV() + (size_t)i * npad + 8 * ct + 2 * q) : make_double2(0.0, 0.0);
+        }
         if (i < T) {
             cp_async_wait<0>();
             __syncwarp();
-            const double *wb = c.wbuf + (size_t)(i & 1) * mpad;
+            const double *wb = c.wbuf() + (i & 1) * mpad + q;
             if (i + 1 < T) {
-                double *wn = c.wbuf + (size_t)((i + 1) & 1) * mpad;
-                const double *src = c.WV + (size_t)(i + 1) * mpad;
+                double *wn = c.wbuf() + ((i + 1) & 1) * mpad;
+                const double *src = c.WV() + (size_t)(i + 1) * mpad;
                 for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(wn + 2 * ch, src + 2 * ch);
             }
             cp_async_commit();
-            // B diag(w_i) B'
-#pragma unroll 2
+            // B diag(w_i) B'  (rows >= n of B read finite junk that only reaches unused rows / columns of S)
+            const double *pB[CT];
+#pragma unroll
+            for (int rt = 0; rt < CT; ++rt) pB[rt] = c.sB() + (size_t)(8 * rt + gq) * c.LDB + q;
+#pragma unroll 4
             for (int kk = 0; kk < c.MK; ++kk) {
-                const int j = 4 * kk + q;
-                const double wv = wb[j];
+                const double wv = wb[4 * kk];
                 double fr[CT];
 #pragma unroll
-                for (int rt = 0; rt < CT; ++rt) fr[rt] = ldp(c.sB + (size_t)(8 * rt + gq) * c.LDB + j, 8 * rt + gq < n);
+                for (int rt = 0; rt < CT; ++rt) fr[rt] = pB[rt][4 * kk];
 #pragma unroll
                 for (int rt = 0; rt < CT; ++rt) {
                     const double a = fr[rt] * wv;
@@ -582,37 +774,22 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c)
             }
         }
         {   // + iterate-independent part of Y[i,i]; rhs row <- -beta_i
-            const int yd = c.ydi[i];
-            if (yd >= 0) {
-                const double *Yd = c.ypool + (size_t)yd * nn;
 #pragma unroll
-                for (int rt = 0; rt < CT; ++rt) {
-                    const int r = 8 * rt + gq;
+            for (int rt = 0; rt < CT; ++rt)
 #pragma unroll
-                    for (int ct = 0; ct <= rt; ++ct) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int cc = 8 * ct + 2 * q + e;
-                            if (r < n && cc <= r) sacc[rt][ct][e] += __ldg(Yd + (size_t)r * n + cc);
-                        }
-                    }
-                }
-            }
+                for (int ct = 0; ct <= rt; ++ct) { sacc[rt][ct][0] += ydv[rt][ct][0]; sacc[rt][ct][1] += ydv[rt][ct][1]; }
             if (yrow) {
 #pragma unroll
-                for (int ct = 0; ct < CT; ++ct) {
-                    const double2 y = *reinterpret_cast<const double2 *>(c.YV + (size_t)i * npad + 8 * ct + 2 * q);
-                    sacc[RT - 1][ct][0] = y.x;
-                    sacc[RT - 1][ct][1] = y.y;
-                }
+                for (int ct = 0; ct < CT; ++ct) { sacc[RT - 1][ct][0] = yrv[ct].x; sacc[RT - 1][ct][1] = yrv[ct].y; }
             }
         }
         if (up1) {
+            const double *p = bL1 + gq * LD + q;
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
                 double fr[RT];
 #pragma unroll
-                for (int rt = 0; rt < RT; ++rt) fr[rt] = ldp(bL1 + (8 * rt + gq) * LD + 4 * kk + q, 8 * rt + gq <= n);
+                for (int rt = 0; rt < RT; ++rt) fr[rt] = p[8 * rt * LD + 4 * kk];
 #pragma unroll
                 for (int rt = 0; rt < RT; ++rt) {
                     const double a = dneg(fr[rt]);
@@ -623,11 +800,12 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c)
             }
         }
         if (up2) {
+            const double *p = bL2pp + gq * LD + q;
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
                 double fr[RT];
 #pragma unroll
-                for (int rt = 0; rt < RT; ++rt) fr[rt] = ldp(bL2pp + (8 * rt + gq) * LD + 4 * kk + q, 8 * rt + gq <= n);
+                for (int rt = 0; rt < RT; ++rt) fr[rt] = p[8 * rt * LD + 4 * kk];
 #pragma unroll
                 for (int rt = 0; rt < RT; ++rt) {
                     const double a = dneg(fr[rt]);
@@ -637,140 +815,189 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c)
                 }
             }
         }
-        // S -> work block (row per lane layout for the factorization); rhs row stays in registers
-        double rhsv[CT][2];
-#pragma unroll
-        for (int ct = 0; ct < CT; ++ct) { rhsv[ct][0] = sacc[RT - 1][ct][0]; rhsv[ct][1] = sacc[RT - 1][ct][1]; }
-#pragma unroll
-        for (int rt = 0; rt < CT; ++rt) {
-            const int r = 8 * rt + gq;
-#pragma unroll
-            for (int ct = 0; ct <= rt; ++ct) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int cc = 8 * ct + 2 * q + e;
-                    if (r < n && cc <= r) bW[r * LDS_ + cc] = sacc[rt][ct][e];
-                }
-            }
-        }
-        __syncwarp();
-        // ================= phase B: L_i, inv(L_i) =================
-        const int info = warp_potrf_inverse<NPOT>(bW, n, c.gLi + (size_t)i * c.NN, lane);
-        if (info) return i + 1;
-        __syncwarp();
-        // ================= phase C: L1_i, y_i, L2_i =================
-        double macc[RT][CT][2];
+        PROF_T(8);
+        // ================= phase B: L_i and inv(L_i) on the accumulator tiles =================
+        // the iterate-independent part of Y[i+1,i] is requested now and consumed in phase C
+        double macc[CT][CT][2];
         {
             const int y1 = c.y1i[i];
             const double *Y1 = c.ypool + (size_t)(y1 >= 0 ? y1 : 0) * nn;
             const bool ld1 = has1 && (y1 >= 0);
 #pragma unroll
-            for (int rt = 0; rt < RT; ++rt) {
+            for (int rt = 0; rt < CT; ++rt) {
                 const int r = 8 * rt + gq;
 #pragma unroll
                 for (int ct = 0; ct < CT; ++ct) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int cc = 8 * ct + 2 * q + e;
-                        macc[rt][ct][e] = (ld1 && r < n && cc < n) ? __ldg(Y1 + (size_t)r * n + cc) : 0.0;
+                        macc[rt][ct][e] = (ld1 && r < n && cc < n) ? __ldg(Y1 + r * n + cc) : 0.0;
                     }
                 }
             }
         }
-        if (has1 && up1 && c.a2) {
+        double linv[CT][CT][2];                              // inv(L_i) tiles (rt, ct <= rt)
+        int info = 0;
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                double fa[RT], fb[CT];
+        for (int kb = 0; kb < CT; ++kb) {
+            const int nv = min(8, n - 8 * kb);
+            if (nv < 8) {                                    // columns >= n of the last diagonal tile: identity
 #pragma unroll
-                for (int rt = 0; rt < RT; ++rt) fa[rt] = dneg(ldp(bL2p + (8 * rt + gq) * LD + 4 * kk + q, 8 * rt + gq < n));
+                for (int e = 0; e < 2; ++e) {
+                    const int cg = 2 * q + e;
+                    if (cg >= nv) sacc[kb][kb][e] = (gq == cg) ? 1.0 : 0.0;
+                }
+            }
+            const int inf = diag8(sacc[kb][kb], linv[kb][kb], nv, gq, q);
+            if (inf && !info) info = 8 * kb + inf;
+            if (nv < 8 && gq >= nv) { linv[kb][kb][0] = 0.0; linv[kb][kb][1] = 0.0; }
 #pragma unroll
-                for (int ct = 0; ct < CT; ++ct) fb[ct] = ldp(bL1 + (8 * ct + gq) * LD + 4 * kk + q, 8 * ct + gq < n);
+            for (int rt = kb + 1; rt < RT; ++rt) {           // panel: L[rt][kb] = S[rt][kb] inv(L_kk)'
+                double o[2] = {0.0, 0.0};
+                mma_xt(o, sacc[rt][kb], linv[kb][kb]);
+                sacc[rt][kb][0] = o[0]; sacc[rt][kb][1] = o[1];
+            }
 #pragma unroll
-                for (int rt = 0; rt < RT; ++rt)
+            for (int rt = kb + 1; rt < RT; ++rt) {           // trailing update
+                const double nx[2] = {dneg(sacc[rt][kb][0]), dneg(sacc[rt][kb][1])};
 #pragma unroll
-                    for (int ct = 0; ct < CT; ++ct) dmma(macc[rt][ct], fa[rt], fb[ct]);
+                for (int ct = kb + 1; ct < CT; ++ct)
+                    if (ct <= rt) mma_xt(sacc[rt][ct], nx, sacc[ct][kb]);
             }
         }
-        if (yrow) {
+        if (info) return i + 1;
+        {   // inv(L) off-diagonal tiles, row by row from the diagonal leftwards:
+            //   inv(L)[rt][ct] = -(sum_{j=ct+1..rt} inv(L)[rt][j] L[j][ct]) inv(L_ct,ct)
+            double lt[CT][CT][2], xdt[CT][2];
 #pragma unroll
-            for (int ct = 0; ct < CT; ++ct) { macc[RT - 1][ct][0] = rhsv[ct][0]; macc[RT - 1][ct][1] = rhsv[ct][1]; }
+            for (int j = 1; j < CT; ++j)
+#pragma unroll
+                for (int ct = 0; ct < j; ++ct) tile_T(lt[j][ct], sacc[j][ct], gq, q);
+#pragma unroll
+            for (int ct = 0; ct + 1 < CT; ++ct) tile_T(xdt[ct], linv[ct][ct], gq, q);
+#pragma unroll
+            for (int rt = 1; rt < CT; ++rt) {
+#pragma unroll
+                for (int ct = rt - 1; ct >= 0; --ct) {
+                    double z[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int j = ct + 1; j <= rt; ++j) mma_xt(z, linv[rt][j], lt[j][ct]);
+                    const double nz[2] = {dneg(z[0]), dneg(z[1])};
+                    linv[rt][ct][0] = linv[rt][ct][1] = 0.0;
+                    mma_xt(linv[rt][ct], nz, xdt[ct]);
+                }
+            }
         }
-        __syncwarp();                                        // every read of L1_{i-1} is done: its block receives L1_i
+        // y_i: row n of the L tiles (columns >= n are not part of y)
         double yv[CT][2];
 #pragma unroll
-        for (int rt = 0; rt < RT; ++rt) {
-            if (has1 || rt == RT - 1) {
-                const int r = 8 * rt + gq;
+        for (int ct = 0; ct < CT; ++ct) {
+            yv[ct][0] = ((ct < CT - 1) || nok0) ? sacc[RT - 1][ct][0] : 0.0;
+            yv[ct][1] = ((ct < CT - 1) || nok1) ? sacc[RT - 1][ct][1] : 0.0;
+        }
+        // inv(L_i) -> global scratch (row-major, leading dimension NPOT; tiles above the diagonal are never written)
+        {
+            double *g = c.gLi() + (size_t)i * (NPOT * NPOT) + gq * NPOT + 2 * q;
+#pragma unroll
+            for (int rt = 0; rt < CT; ++rt)
+#pragma unroll
+                for (int ct = 0; ct <= rt; ++ct) {
+                    const bool rok = (rt < CT - 1) || (8 * rt + gq < NPOT);
+                    const bool ok = rok && ((ct < CT - 1) || cok0);
+                    if (ok) *reinterpret_cast<double2 *>(g + 8 * rt * NPOT + 8 * ct) = make_double2(linv[rt][ct][0], linv[rt][ct][1]);
+                }
+            if (yrow) {
+#pragma unroll
+                for (int ct = 0; ct < CT; ++ct) *reinterpret_cast<double2 *>(c.YV() + (size_t)i * npad + 8 * ct + 2 * q) = make_double2(yv[ct][0], yv[ct][1]);
+            }
+        }
+        PROF_T(9);
+        // ================= phase C: L1_i = (Y1 - L2_{i-1} L1_{i-1}') inv(L_i)' ,  L2_i = Y2 inv(L_i)' =================
+        if (has1) {
+            if (up1 && c.a2) {
+                const double *pa = bL2p + gq * LD + q, *pb = bL1 + gq * LD + q;
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    double fa[CT], fb[CT];
+#pragma unroll
+                    for (int rt = 0; rt < CT; ++rt) { fa[rt] = dneg(pa[8 * rt * LD + 4 * kk]); fb[rt] = pb[8 * rt * LD + 4 * kk]; }
+#pragma unroll
+                    for (int rt = 0; rt < CT; ++rt)
+#pragma unroll
+                        for (int ct = 0; ct < CT; ++ct) dmma(macc[rt][ct], fa[rt], fb[ct]);
+                }
+            }
+            __syncwarp();                                    // every read of L1_{i-1} is done: its block receives L1_i
+            double *g = c.gL1() + (size_t)i * (NPOT * NPOT) + gq * NPOT + 2 * q;
+            double *s = bL1 + gq * LD + 2 * q;
+#pragma unroll
+            for (int rt = 0; rt < CT; ++rt) {
+                const bool rok = (rt < CT - 1) || (8 * rt + gq < n);
 #pragma unroll
                 for (int ct = 0; ct < CT; ++ct) {
                     double o[2] = {0.0, 0.0};
 #pragma unroll
-                    for (int jt = 0; jt <= ct; ++jt) {
-                        const double2 lf = *reinterpret_cast<const double2 *>(bW + (ct * (ct + 1) / 2 + jt) * 64 + 2 * lane);
-                        dmma(o, macc[rt][jt][0], lf.x);
-                        dmma(o, macc[rt][jt][1], lf.y);
-                    }
-                    if (rt == RT - 1) { yv[ct][0] = o[0]; yv[ct][1] = o[1]; }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = 8 * ct + 2 * q + e;
-                        if (r <= n && cc < NPOT) bL1[r * LD + cc] = o[e];
-                        if (has1 && r < n && cc < n) c.gL1[(size_t)i * c.NN + (size_t)r * n + cc] = o[e];
-                        if (r == n && cc < n) c.YV[(size_t)i * npad + cc] = o[e];
-                    }
+                    for (int jt = 0; jt <= ct; ++jt) mma_xt(o, macc[rt][jt], linv[ct][jt]);
+                    const bool c0 = (ct < CT - 1) || cok0, c1 = (ct < CT - 1) || cok1;
+                    if (rok && c0) s[8 * rt * LD + 8 * ct] = o[0];
+                    if (rok && c1) s[8 * rt * LD + 8 * ct + 1] = o[1];
+                    if (rok && c0) *reinterpret_cast<double2 *>(g + 8 * rt * NPOT + 8 * ct) = make_double2(o[0], o[1]);
                 }
+            }
+        } else {
+            __syncwarp();
+        }
+        if (yrow) {                                          // row n of the L1 block carries y_i
+            double *s = bL1 + n * LD + 2 * q;
+#pragma unroll
+            for (int ct = 0; ct < CT; ++ct) {
+                if ((ct < CT - 1) || cok0) s[8 * ct] = yv[ct][0];
+                if ((ct < CT - 1) || cok1) s[8 * ct + 1] = yv[ct][1];
             }
         }
         if (has2) {
             const bool y2ok = (c.y2i[i] >= 0);
-            double nqi[CT][2];                                // -inv(2Q)(k) for k = 8 jt + 2 q + e
+            double *g = c.gL2() + (size_t)i * (NPOT * NPOT) + gq * NPOT + 2 * q;
+            double *s = bL2pp + gq * LD + 2 * q;
+            double nqi[CT][2];                                // -inv(2Q)(k) for k = 8 jt + 2 q + e  (0 for k >= n)
 #pragma unroll
-            for (int jt = 0; jt < CT; ++jt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = 8 * jt + 2 * q + e;
-                    nqi[jt][e] = (k < n) ? -c.sQi[k] : 0.0;
-                }
+            for (int jt = 0; jt < CT; ++jt) {
+                nqi[jt][0] = y2ok ? -c.sQi()[8 * jt + 2 * q] : 0.0;
+                nqi[jt][1] = y2ok ? -c.sQi()[8 * jt + 2 * q + 1] : 0.0;
+            }
+            const double *pa2 = c.sA2() + gq * LD + 2 * q;
 #pragma unroll
             for (int rt = 0; rt < CT; ++rt) {
-                const int r = 8 * rt + gq;
-                double af[CT][2];
+                const bool rok = (rt < CT - 1) || (8 * rt + gq < n);
+                double af[CT][2];                             // Y2 = -A2 inv(2Q) : rows of A2, k in pair order
 #pragma unroll
-                for (int jt = 0; jt < CT; ++jt)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int k = 8 * jt + 2 * q + e;
-                        af[jt][e] = ldp(c.sA2 + (size_t)r * LD + k, y2ok && r < n && k < n) * nqi[jt][e];   // Y2 = -A2 inv(2Q)
-                    }
+                for (int jt = 0; jt < CT; ++jt) {
+                    af[jt][0] = pa2[8 * rt * LD + 8 * jt] * nqi[jt][0];
+                    af[jt][1] = pa2[8 * rt * LD + 8 * jt + 1] * nqi[jt][1];
+                }
 #pragma unroll
                 for (int ct = 0; ct < CT; ++ct) {
                     double o[2] = {0.0, 0.0};
 #pragma unroll
-                    for (int jt = 0; jt <= ct; ++jt) {
-                        const double2 lf = *reinterpret_cast<const double2 *>(bW + (ct * (ct + 1) / 2 + jt) * 64 + 2 * lane);
-                        dmma(o, af[jt][0], lf.x);
-                        dmma(o, af[jt][1], lf.y);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = 8 * ct + 2 * q + e;
-                        if (r < n && cc < NPOT) bL2pp[r * LD + cc] = o[e];
-                        if (r < n && cc < n) c.gL2[(size_t)i * c.NN + (size_t)r * n + cc] = o[e];
-                    }
+                    for (int jt = 0; jt <= ct; ++jt) mma_xt(o, af[jt], linv[ct][jt]);
+                    const bool c0 = (ct < CT - 1) || cok0, c1 = (ct < CT - 1) || cok1;
+                    if (rok && c0) s[8 * rt * LD + 8 * ct] = o[0];
+                    if (rok && c1) s[8 * rt * LD + 8 * ct + 1] = o[1];
+                    if (rok && c0) *reinterpret_cast<double2 *>(g + 8 * rt * NPOT + 8 * ct) = make_double2(o[0], o[1]);
                 }
             }
             if (yrow) {                                       // row n of the L2 block carries y_i as well
+                double *sy = bL2pp + n * LD + 2 * q;
 #pragma unroll
-                for (int ct = 0; ct < CT; ++ct)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = 8 * ct + 2 * q + e;
-                        if (cc < NPOT) bL2pp[n * LD + cc] = yv[ct][e];
-                    }
+                for (int ct = 0; ct < CT; ++ct) {
+                    if ((ct < CT - 1) || cok0) sy[8 * ct] = yv[ct][0];
+                    if ((ct < CT - 1) || cok1) sy[8 * ct + 1] = yv[ct][1];
+                }
             }
         }
         { double *t2 = bL2p; bL2p = bL2pp; bL2pp = t2; }
         __syncwarp();
+        PROF_T(10);
     }
     cp_async_wait<0>();
     return 0;
@@ -778,71 +1005,74 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c)
 
 // ---------------------------------------------------------------------------------------------
 // Backward substitution  dnu_i = inv(L_i)' (y_i - L1_i' dnu_{i+1} - L2_i' dnu_{i+2})  (inf_newton_solver.m:32).
-// The factor comes back from the global scratch through a 4-slot cp.async ring (3 entries per stage).
+// The factor comes back from the global scratch through a 3-slot cp.async ring (3 entries per stage);
+// lane k owns component k: its column of each matrix is read into registers, then 4 independent FMA chains.
+// Rows / columns >= n of the stored matrices are zero (never written), so nothing is predicated.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ring_issue(const WCtx &c, double *const (&slot)[4], const int e, const int nent)
+template <int NPOT>
+__device__ __forceinline__ void ring_issue(const WCtx &c, const int e, const int nent)
 {
     if (e < nent) {
         const int i = c.NB - 1 - e / 3, kind = e % 3;
         const bool on = (kind == 2) || (kind == 0 && i + 1 < c.NB) || (kind == 1 && i + 2 < c.NB && c.a2);
         if (on) {
-            const double *src = (kind == 0 ? c.gL1 : (kind == 1 ? c.gL2 : c.gLi)) + (size_t)i * c.NN;
-            double *dst = slot[e & 3];
-            for (int ch = c.lane; ch < c.NN / 2; ch += 32) cp_async16(dst + 2 * ch, src + 2 * ch);
+            const double *src = (kind == 0 ? c.gL1() : (kind == 1 ? c.gL2() : c.gLi())) + (size_t)i * (NPOT * NPOT);
+            double *dst = c.wsm + (e % 3) * (NPOT * NPOT);
+            for (int ch = c.lane; ch < NPOT * NPOT / 2; ch += 32) cp_async16(dst + 2 * ch, src + 2 * ch);
         }
     }
     cp_async_commit();
 }
 
+template <int NPOT>
 __device__ __forceinline__ void backward_sweep(const WCtx &c)
 {
-    const int n = c.n, NB = c.NB, npad = c.npad, lane = c.lane;
-    double *const slot[4] = {c.blk0, c.blk1, c.blk2, c.bW};
-    double *vec = c.wbuf;                                   // [3][32] dnu ring + [32] tmp
+    constexpr int npad = 8 * ((NPOT + 7) / 8);
+    const int n = c.n, NB = c.NB, lane = c.lane;
+    double *vec = c.wsm + 3 * (NPOT * NPOT);                 // [3][32] dnu ring + [32] tmp (behind the 3 ring slots)
     const int nent = 3 * NB;
+    const bool act = lane < n;
     __syncwarp();
-    for (int e = 0; e < 4; ++e) ring_issue(c, slot, e, nent);
-    double acc = 0.0;
+    vec[lane] = 0.0; vec[32 + lane] = 0.0; vec[64 + lane] = 0.0; vec[96 + lane] = 0.0;
+    for (int e = 0; e < 3; ++e) ring_issue<NPOT>(c, e, nent);
+    double acc = 0.0, yi = 0.0;
     for (int e = 0; e < nent; ++e) {
         const int i = NB - 1 - e / 3, kind = e % 3;
-        cp_async_wait<3>();
+        if (kind == 0) yi = act ? c.YV()[(size_t)i * npad + lane] : 0.0;       // consumed two entries later
+        cp_async_wait<2>();
         __syncwarp();
-        const double *M = slot[e & 3];
-        if (kind == 0) {
-            acc = 0.0;
-            if (i + 1 < NB && lane < n) {
-                const double *d1 = vec + ((i + 1) % 3) * 32;
-                double s0 = 0.0, s1 = 0.0;
-                int r = 0;
-                for (; r + 1 < n; r += 2) { s0 = fma(M[r * n + lane], d1[r], s0); s1 = fma(M[(r + 1) * n + lane], d1[r + 1], s1); }
-                if (r < n) s0 = fma(M[r * n + lane], d1[r], s0);
-                acc = s0 + s1;
-            }
-        } else if (kind == 1) {
-            if (i + 2 < NB && c.a2 && lane < n) {
-                const double *d2 = vec + ((i + 2) % 3) * 32;
-                double s0 = 0.0, s1 = 0.0;
-                int r = 0;
-                for (; r + 1 < n; r += 2) { s0 = fma(M[r * n + lane], d2[r], s0); s1 = fma(M[(r + 1) * n + lane], d2[r + 1], s1); }
-                if (r < n) s0 = fma(M[r * n + lane], d2[r], s0);
-                acc += s0 + s1;
+        const double *M = c.wsm + (e % 3) * (NPOT * NPOT) + (lane < NPOT ? lane : 0);
+        if (kind < 2) {
+            if (kind == 0) acc = 0.0;
+            const bool on = (kind == 0) ? (i + 1 < NB) : (i + 2 < NB && c.a2);
+            if (on) {
+                const double *dv = vec + ((i + 1 + kind) % 3) * 32;
+                double mv[NPOT];
+#pragma unroll
+                for (int r = 0; r < NPOT; ++r) mv[r] = M[r * NPOT];
+                double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < NPOT; ++r) s[r & 3] = fma(mv[r], dv[r], s[r & 3]);
+                acc += (s[0] + s[1]) + (s[2] + s[3]);
             }
         } else {
             double *tmp = vec + 96;
-            if (lane < n) tmp[lane] = c.YV[(size_t)i * npad + lane] - acc;
+            double mv[NPOT];
+#pragma unroll
+            for (int r = 0; r < NPOT; ++r) mv[r] = M[r * NPOT];
+            if (act) tmp[lane] = yi - acc;
             __syncwarp();
-            if (lane < n) {
-                double s0 = 0.0, s1 = 0.0;
-                int r = lane;
-                for (; r + 1 < n; r += 2) { s0 = fma(M[r * n + lane], tmp[r], s0); s1 = fma(M[(r + 1) * n + lane], tmp[r + 1], s1); }
-                if (r < n) s0 = fma(M[r * n + lane], tmp[r], s0);
-                const double d = s0 + s1;
+            double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < NPOT; ++r) s[r & 3] = fma(mv[r], tmp[r], s[r & 3]);
+            const double d = (s[0] + s[1]) + (s[2] + s[3]);
+            if (act) {
                 vec[(i % 3) * 32 + lane] = d;
-                c.DNU[(size_t)i * npad + lane] = d;
+                c.DNU()[(size_t)i * npad + lane] = d;
             }
         }
         __syncwarp();                                        // slot consumed by every lane
-        ring_issue(c, slot, e + 4, nent);
+        ring_issue<NPOT>(c, e + 3, nent);
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -857,22 +1087,21 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
     extern __shared__ double smem[];
     const int n = S.n, m = S.m, T = S.T;
     const WGeom G = WGeom::make(n, m, T);
-    const WsW L = WsW::make(G);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
-    constexpr int LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4;
+    constexpr int LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, npad = 8 * ((NPOT + 7) / 8);
 
-    // ---- shared memory: zero everything (padding and overrun reads must see finite values), then the constants ----
+    // ---- shared memory: zero everything (overrun reads must see finite values), then the constants ----
     {
-        const size_t tot = G.const_doubles + (size_t)nwarps * G.warp_doubles;
+        const size_t tot = G.smem_doubles(nwarps);
         for (size_t e = tid; e < tot; e += blockDim.x) smem[e] = 0.0;
     }
     __syncthreads();
     double *sB = smem;
     double *sA1 = sB + (size_t)n * G.LDB;
-    double *sA2 = sA1 + (size_t)n * LD + 8;
-    double *sUmax = sA2 + (size_t)n * LD + 8;
+    double *sA2 = sA1 + (size_t)n * LD;
+    double *sUmax = sA2 + (size_t)n * LD;
     double *sUmin = sUmax + G.mpad, *sR2 = sUmin + G.mpad, *sRl = sR2 + G.mpad;
-    double *sQ2 = sRl + G.mpad, *sQl = sQ2 + 2 * G.npad, *sQi = sQl + 2 * G.npad;
+    double *sQ2 = sRl + G.mpad, *sQl = sQ2 + 2 * npad, *sQi = sQl + 2 * npad;
     for (int e = tid; e < n * m; e += blockDim.x) { const int k = e % n, j = e / n; sB[(size_t)k * G.LDB + j] = S.B[e]; }      // B is column-major n x m
     for (int e = tid; e < n * n; e += blockDim.x) {
         const int k = e % n, kc = e / n;
@@ -885,29 +1114,26 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
         sR2[j] = (j < m) ? S.r2[j] : 1.0;
         sRl[j] = (j < m) ? S.rl[j] : 0.0;
     }
-    for (int k = tid; k < G.npad; k += blockDim.x) {
+    for (int k = tid; k < npad; k += blockDim.x) {
         const bool ok = k < n;
-        sQ2[k] = ok ? S.q2[k] : 0.0;  sQ2[G.npad + k] = ok ? S.q2f[k] : 0.0;
-        sQl[k] = ok ? S.ql[k] : 0.0;  sQl[G.npad + k] = ok ? S.qfl[k] : 0.0;
-        sQi[k] = ok ? S.qi[k] : 0.0;  sQi[G.npad + k] = ok ? S.qif[k] : 0.0;
+        sQ2[k] = ok ? S.q2[k] : 0.0;  sQ2[npad + k] = ok ? S.q2f[k] : 0.0;
+        sQl[k] = ok ? S.ql[k] : 0.0;  sQl[npad + k] = ok ? S.qfl[k] : 0.0;
+        sQi[k] = ok ? S.qi[k] : 0.0;  sQi[npad + k] = ok ? S.qif[k] : 0.0;
     }
     __syncthreads();
 
     WCtx c;
     c.n = n; c.m = m; c.T = T; c.NB = T + (A.has_xf ? 1 : 0); c.a2 = S.has_a2; c.has_xf = A.has_xf;
-    c.mpad = G.mpad; c.MK = G.MK; c.MT8 = G.MT8; c.npad = G.npad; c.LDB = G.LDB; c.NTT = G.NTT; c.NN = G.NN;
+    c.mpad = G.mpad; c.MK = G.MK; c.MT8 = G.MT8; c.npad = npad; c.LDB = G.LDB; c.NTT = G.NTT;
     c.lane = lane; c.gq = lane >> 2; c.q = lane & 3;
     c.kappa = A.kappa;
-    c.sB = sB; c.sA1 = sA1; c.sA2 = sA2; c.sUmax = sUmax; c.sUmin = sUmin; c.sR2 = sR2; c.sRl = sRl; c.sQ2 = sQ2; c.sQl = sQl; c.sQi = sQi;
-    double *wsm = smem + G.const_doubles + (size_t)wid * G.warp_doubles;
-    c.blk0 = wsm; c.blk1 = wsm + G.BLK; c.blk2 = wsm + 2 * G.BLK; c.bW = wsm + 3 * G.BLK; c.wbuf = c.bW + G.WSZ;
+    c.smem = smem; c.oA1 = (int)(sA1 - smem); c.oA2 = (int)(sA2 - smem); c.oU = (int)(sUmax - smem); c.oQ = (int)(sQ2 - smem);
+    c.wsm = smem + G.const_doubles + (size_t)wid * G.warp_doubles; c.BLK = G.BLK;
     double *ws = A.ws + ((size_t)blockIdx.x * nwarps + wid) * A.ws_stride;
-    c.HU = ws + L.HU; c.HDU = ws + L.HDU; c.DU = ws + L.DU; c.WV = ws + L.WV; c.DB = ws + L.DB; c.RDU = ws + L.RDU;
-    c.HX = ws + L.HX; c.HDX = ws + L.HDX; c.DX = ws + L.DX; c.RDX = ws + L.RDX;
-    c.YV = ws + L.YV; c.DNU = ws + L.DNU; c.BV = ws + L.BV;
-    c.gLi = ws + L.Li; c.gL1 = ws + L.L1; c.gL2 = ws + L.L2;
+    c.ws = ws; c.tu = G.TP8 * G.mpad; c.tx = G.TP8 * npad; c.tb = (G.TP8 + 1) * npad; c.bl = (T + 1) * G.NN; c.pp = 0;
     c.ypool = S.ypool; c.ydi = S.ydi; c.y1i = S.y1i; c.y2i = S.y2i;
-    const int NB = c.NB, mpad = G.mpad, npad = G.npad;
+    c.xmin = S.xmin; c.xmax = S.xmax;
+    const int NB = c.NB, mpad = G.mpad;
 
     for (;;) {
         int b = 0;
@@ -915,47 +1141,55 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
         b = __shfl_sync(FULL, b, 0);
         if (b >= A.nbatch) break;
         PROF_DECL
-        c.UC = ws + L.UC; c.UT = ws + L.UT; c.XC = ws + L.XC; c.XT = ws + L.XT; c.RP = ws + L.RP; c.RPT = ws + L.RPT;
-        const double *x0 = A.x0 + (size_t)b * n;
-        const double *x0p = A.x0_pre ? A.x0_pre + (size_t)b * n : nullptr;
+        c.pp = 0;
+        c.U0 = A.cold ? nullptr : A.U0 + (size_t)b * m * T;
+        c.X0 = A.cold ? nullptr : A.X0 + (size_t)b * n * T;
 
-        // ---- b (fast_mpc_eq_const.m:39,44,47,68), initial iterate (fast_mpc_init.m:12-26) ----
-        if (lane < n) {
-            double s0 = 0.0, s1 = 0.0;
-            for (int kc = 0; kc < n; ++kc) {
-                const double xv = x0[kc];
-                s0 = fma(sA1[(size_t)lane * LD + kc], xv, s0);
-                if (S.has_a2) { s0 = fma(sA2[(size_t)lane * LD + kc], x0p[kc], s0); s1 = fma(sA2[(size_t)lane * LD + kc], xv, s1); }
-            }
-            for (int i = 0; i < NB; ++i) {
-                double v;
-                if (i < T) {
-                    v = A.w ? A.w[(size_t)b * T * n + (size_t)i * n + lane] : 0.0;
-                    if (i == 0) v += s0;
-                    else if (i == 1) v += s1;
-                } else {
-                    v = A.xf[(size_t)b * n + lane];
-                }
-                c.BV[(size_t)i * npad + lane] = v;
-            }
-        }
+        // ---- b (fast_mpc_eq_const.m:39,44,47,68): lane k owns row k; x0 / x0_pre broadcast by shuffles;
+        //      the dual start nu goes to the (column padded) DNU buffer ----
         {
-            const double *u0 = A.cold ? nullptr : A.U0 + (size_t)b * m * T;
-            const double *xx0 = A.cold ? nullptr : A.X0 + (size_t)b * n * T;
-            for (int e = lane; e < T * mpad; e += 32) {
-                const int t = e / mpad, j = e - t * mpad;
-                c.UC[e] = (j < m) ? (A.cold ? (S.umin[j] + S.umax[j]) / 2 : u0[(size_t)t * m + j]) : 0.0;
+            const double x0v = (lane < n) ? A.x0[(size_t)b * n + lane] : 0.0;
+            const double x0pv = (lane < n && A.x0_pre) ? A.x0_pre[(size_t)b * n + lane] : 0.0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            const double *r1 = sA1 + (size_t)(lane < n ? lane : 0) * LD, *r2 = sA2 + (size_t)(lane < n ? lane : 0) * LD;
+#pragma unroll
+            for (int kc = 0; kc < NPOT; ++kc) {
+                const double xv = __shfl_sync(FULL, x0v, kc), xpv = __shfl_sync(FULL, x0pv, kc);   // 0 for kc >= n
+                const double a1 = r1[kc], a2v = r2[kc];
+                s0 = fma(a1, xv, s0);
+                s2 = fma(a2v, xpv, s2);
+                s1 = fma(a2v, xv, s1);
             }
-            for (int e = lane; e < T * npad; e += 32) {
-                const int t = e / npad, k = e - t * npad;
-                c.XC[e] = (k < n) ? (A.cold ? (S.xmin[k] + S.xmax[k]) / 2 : xx0[(size_t)t * n + k]) : 0.0;
+            s0 += s2;
+            const double *nu0 = A.nu0 + (size_t)b * NB * n;
+            for (int i0 = 0; i0 < NB; i0 += 4) {
+                double wv[4], nv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u;
+                    wv[u] = nv[u] = 0.0;
+                    if (lane < n && i < NB) {
+                        if (i < T) wv[u] = A.w ? A.w[(size_t)b * T * n + (size_t)i * n + lane] : 0.0;
+                        else wv[u] = A.xf[(size_t)b * n + lane];
+                        nv[u] = nu0[(size_t)i * n + lane];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u;
+                    if (lane < n && i < NB) {
+                        double v = wv[u];
+                        if (i < T) { if (i == 0) v += s0; else if (i == 1) v += s1; }
+                        c.BV()[(size_t)i * npad + lane] = v;
+                        c.DNU()[(size_t)i * npad + lane] = nv[u];
+                    }
+                }
             }
         }
         __syncwarp();
         double ssd, ssp;
-        pass_Cv<NPOT, K_RP>(c, 0.0, ssd, ssp);                         // r_p = C z - b
-        __syncwarp();
-        pass_Ct<NPOT, 0>(c, A.nu0 + (size_t)b * NB * n, n);            // images of the dual start nu
+        pass_Cv<NPOT, K_RP>(c, 0.0, ssd, ssp);                         // z <- start ; r_p = C z - b
+        pass_Ct<NPOT, 0>(c);                                           // images of the dual start nu
         __syncwarp();
         PROF_T(0);
 
@@ -969,12 +1203,12 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
             if (!isfinite(nr0)) { status = ST_NONFINITE; break; }
             if (nr0 <= A.tol_r && sqrt(tot_p) <= A.tol_p) { status = ST_EARLY_EXIT; break; }
             __syncwarp();
-            const int fail = forward_sweep<NPOT, RT>(c);
+            const int fail = forward_sweep<NPOT, RT>(c PROF_ARGS);
             PROF_T(2);
             if (fail) { status = ST_NOT_PD; break; }
-            backward_sweep(c);
+            backward_sweep<NPOT>(c);
             PROF_T(3);
-            pass_Ct<NPOT, 1>(c, c.DNU, npad);                          // dz = inv(Phi)(-r_d - C' dnu)
+            pass_Ct<NPOT, 1>(c);                                       // dz = inv(Phi)(-r_d - C' dnu)
             __syncwarp();
             PROF_T(4);
             // ---- backtracking on ||[r_p; r_d]||, d frozen (backtracking_inf_newton.m:2-11) ----
@@ -992,19 +1226,28 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
                 ++nh;
             }
             PROF_T(5);
-            // accept: swap iterate / r_p buffers, advance the dual images
-            { double *s1 = c.UC; c.UC = c.UT; c.UT = s1; double *s2 = c.XC; c.XC = c.XT; c.XT = s2; double *s3 = c.RP; c.RP = c.RPT; c.RPT = s3; }
-            for (int e = lane; e < T * mpad; e += 32) c.HU[e] = __fma_rn(t, c.HDU[e], c.HU[e]);
-            for (int e = lane; e < T * npad; e += 32) c.HX[e] = __fma_rn(t, c.HDX[e], c.HX[e]);
+            // accept: the trial pass left z + t dz, C(z + t dz) - b and the advanced dual images in the *T buffers
+            c.pp ^= 1;
             ++iters;
-            __syncwarp();
-            PROF_T(6);
         }
         __syncwarp();
-        {
+        {   // iterate -> outputs (8 elements in flight per lane)
             double *uo = A.U + (size_t)b * m * T, *xo = A.X + (size_t)b * n * T;
-            for (int e = lane; e < T * m; e += 32) { const int t = e / m, j = e - t * m; uo[e] = c.UC[(size_t)t * mpad + j]; }
-            for (int e = lane; e < T * n; e += 32) { const int t = e / n, k = e - t * n; xo[e] = c.XC[(size_t)t * npad + k]; }
+            const double *pu = c.UC(), *px = c.XC();
+            for (int e0 = lane; e0 < T * m; e0 += 256) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; v[u] = 0.0; if (e < T * m) { const int t = e / m, j = e - t * m; v[u] = pu[(size_t)t * mpad + j]; } }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < T * m) uo[e] = v[u]; }
+            }
+            for (int e0 = lane; e0 < T * n; e0 += 256) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; v[u] = 0.0; if (e < T * n) { const int t = e / n, k = e - t * n; v[u] = px[(size_t)t * npad + k]; } }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < T * n) xo[e] = v[u]; }
+            }
         }
         if (lane == 0) {
             if (A.status) A.status[b] = status;
@@ -1025,11 +1268,11 @@ template <int NPOT, int RT>
 static int config_warp(const WGeom &G, SolveLaunchCfg *cfg, const cudaDeviceProp &prop)
 {
     const size_t avail = prop.sharedMemPerBlockOptin;
-    if (G.const_doubles * 8 + G.warp_doubles * 8 > avail) return -3;
-    int warps = (int)((avail - G.const_doubles * 8) / (G.warp_doubles * 8));
-    if (warps > 8) warps = 8;
+    if (G.smem_doubles(1) * 8 > avail) return -3;
+    int warps = 8;
+    while (warps > 1 && G.smem_doubles(warps) * 8 > avail) --warps;
     if (const char *e = getenv("FMPC_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 1 && v < warps) warps = v; }
-    const size_t smem = (G.const_doubles + (size_t)warps * G.warp_doubles) * 8;
+    const size_t smem = G.smem_doubles(warps) * 8;
     if (cudaFuncSetAttribute(fmpc_solve_kernel_warp<NPOT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
     cfg->grid = prop.multiProcessorCount;
     cfg->block = 32 * warps;
@@ -1040,6 +1283,14 @@ static int config_warp(const WGeom &G, SolveLaunchCfg *cfg, const cudaDeviceProp
     return 0;
 }
 
+#ifdef FMPC_FAST_BUILD          /* compile-time experiments: two instantiations only */
+#define WARP_DISPATCH(G, CALL)                                                                         \
+    switch ((G).NPOT * 8 + (G).RT) {                                                                   \
+    case 8 * 8 + 1: CALL(8, 1); break;                                                                 \
+    case 28 * 8 + 4: CALL(28, 4); break;                                                               \
+    default: break;                                                                                    \
+    }
+#else
 #define WARP_DISPATCH(G, CALL)                                                                         \
     switch ((G).NPOT * 8 + (G).RT) {                                                                   \
     case 8 * 8 + 1: CALL(8, 1); break;                                                                 \
@@ -1053,6 +1304,7 @@ static int config_warp(const WGeom &G, SolveLaunchCfg *cfg, const cudaDeviceProp
     case 32 * 8 + 5: CALL(32, 5); break;                                                               \
     default: break;                                                                                    \
     }
+#endif
 
 int fmpc_warp_config(const DevSys &S, int device, SolveLaunchCfg *cfg)
 {

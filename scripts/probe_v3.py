@@ -9,7 +9,7 @@ from mpc_sensorlessao_b200 import synth
 from oracle import fmpc_ref as fr
 from cases import small_problem, ref_solve, relerr
 
-PH = ["init", "newton_pass", "fwd_sweep", "bwd_sweep", "Ct_pass", "linesearch", "accept", "copyout"]
+PH = ["init", "newton_pass", "fwd_sweep", "bwd_sweep", "Ct_pass", "linesearch", "accept", "copyout", "fwdA", "fwdB_potrf", "fwdC", "x"]
 mode = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
@@ -79,7 +79,7 @@ if mode in ("all", "perf"):
         prof = hb.last_profile()
         if prof.sum() > 0:
             tot = prof[:8].sum()
-            print("phase cycles per solve (warp-local):", {PH[i]: int(prof[i] / nb) for i in range(8)}, "total", int(tot / nb), flush=True)
+            print("phase cycles per solve (warp-local):", {PH[i]: int(prof[i] / nb) for i in range(11)}, "total", int(tot / nb), flush=True)
         if nb == 4096:
             ref = fr.solve_batch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, 0.01, 5, wi['x0'][:64].T, wi['x0_pre'][:64].T, None,
                                  np.concatenate([wi['U0'][:64], wi['X0'][:64]], axis=2).reshape(64, -1).T, wi['nu0'][:64].T)
