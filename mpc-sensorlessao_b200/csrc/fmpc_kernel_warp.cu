@@ -77,8 +77,10 @@ __device__ __forceinline__ double rsqrt_nr(const double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // cubic (Halley) step: y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 : relative error 2^-20 -> ~2^-58; one cheap
+    // quadratic polish brings it to the last bit
     double e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
+    y = fma(y * e, fma(0.375, e, 0.5), y);
     e = fma(-x * y, y, 1.0);
     return fma(0.5 * y, e, y);
 }
@@ -94,6 +96,12 @@ __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// DRAM -> L2 prefetch of `bytes` bytes at p (one 128-byte line per lane and step); no registers are tied up
+__device__ __forceinline__ void l2_prefetch(const double *p, const int bytes, const int lane)
+{
+    const char *b = reinterpret_cast<const char *>(p);
+    for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // The two residual expressions live in ONE place each: the line search compares norms computed by
@@ -147,7 +155,8 @@ struct WGeom {
         g.const_doubles = (g.const_doubles + 1) & ~(size_t)1;
         g.warp_doubles = 3 * (size_t)g.BLK + (size_t)g.WB;
         if (g.warp_doubles < 3 * (size_t)g.NN + 128) g.warp_doubles = 3 * (size_t)g.NN + 128;   // backward ring: 3 slots of NN + vectors
-        g.tail_doubles = 8 * (size_t)g.LDB + 16 * (size_t)g.LD + 8;   // overrun reads of the last rows stay inside the allocation
+        if (g.warp_doubles < 2304) g.warp_doubles = 2304;                                   // u-space stream ring of the passes (4 slots)
+        g.tail_doubles = 8 * (size_t)g.LD + 8;   // overrun reads of the last rows stay inside the allocation
         return g;
     }
     __host__ __device__ size_t smem_doubles(int warps) const { return const_doubles + (size_t)warps * warp_doubles + tail_doubles; }
@@ -233,6 +242,32 @@ struct WCtx {
 enum { K_RP = 0, K_NEWTON = 1, K_TRIAL = 2 };
 
 // ---------------------------------------------------------------------------------------------
+// u-space streams of the passes: chunks of (8 TT rows) x (CW columns) of NA arrays go through a 4-slot cp.async ring in
+// this warp's shared memory (free while no sweep is running).  No registers are tied up by data in flight, the ring
+// runs 4 chunks ahead, and the consumer reads its fragment elements with conflict-free LDS.
+// Slot layout [array][row 0..23][RS], RS chosen so that the fragment reads are conflict-free.
+// ---------------------------------------------------------------------------------------------
+constexpr int STREAM_RD = 4;
+template <int NA, int CW, int RS>
+__device__ __forceinline__ void stream_issue(const WCtx &c, const double *const (&arr)[NA], const int tt0, const int TT, const int ch, const int nch)
+{
+    if (ch < nch) {
+        double *slot = c.wsm + (ch % STREAM_RD) * (NA * 8 * TTMAX * RS);
+        const int rows = 8 * TT;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            const double *src = arr[a] + (size_t)(8 * tt0) * c.mpad + CW * ch;
+            double *dst = slot + a * (8 * TTMAX * RS);
+            for (int p = c.lane; p < rows * (CW / 2); p += 32) {
+                const int row = p / (CW / 2), pc = p - row * (CW / 2);
+                cp_async16(dst + row * RS + 2 * pc, src + (size_t)row * c.mpad + 2 * pc);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Horizon GEMM  acc[t][k] = (B v_u,t + A1 v_x,t-1 + A2 v_x,t-2)[k]  and its three uses
 //   K_RP     : v = z0 (start)     ; UC, XC <- z0 ; RP  = x_t+1 - acc - b      (fast_mpc_init.m:12-26, r_p = C z - b)
 //   K_NEWTON : v = inv(Phi) r_d   ; YV  = r_p - C v ; barrier terms, r_d, norms (inf_newton_KKT_H.m:3-13, :12, :28-29)
@@ -251,6 +286,13 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
     constexpr int XU = 4;
     const int n = c.n, m = c.m, T = c.T, mpad = c.mpad, gq = c.gq, q = c.q, lane = c.lane;
     ss_d = 0.0; ss_p = 0.0;
+    // the u-space streams of this pass were written long ago (they have left L2 for DRAM): pull them back into L2 now,
+    // the register pipeline below then only has to cover L2 latency
+    {
+        const int ub = T * mpad * 8;
+        (void)ub;
+        if (KIND == K_RP) { if (c.U0) l2_prefetch(c.U0, T * m * 8, lane); }
+    }
     // ---- x-space elementwise (linear ownership, XU elements in flight per lane), then visible to the whole warp ----
     {
         const int tot = T * npad;
@@ -322,79 +364,110 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
             tok[tt] = (tt < TT) && (t < T);
             row[tt] = ((tt < TT) ? t : 0) * mpad + q;        // rows of dead tiles alias row 0 (finite data, unused result)
         }
-        // ---- u part: A fragment element (t = 8 tt + gq, j = 4 kk + q) is produced by its owner; kk in pairs ----
-        double cur[2][TTMAX][NA], nxt[2][TTMAX][NA];
-        auto load = [&](double (&bf)[2][TTMAX][NA], const int kp) {
+        // ---- u part: A fragment element (t = 8 tt + gq, j = 4 kk + q) is produced by its owner ----
+        if (KIND == K_RP) {
+            // start of the iterate straight from the caller's arrays (leading dimension m): register pipeline, kk in pairs
+            double cur[2][TTMAX], nxt[2][TTMAX];
+            auto load = [&](double (&bf)[2][TTMAX], const int kp) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j4 = 8 * kp + 4 * h;
+                for (int h = 0; h < 2; ++h) {
+                    const int j4 = 8 * kp + 4 * h;
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt) {
-                    const int idx = row[tt] + j4;
-                    if (KIND == K_RP) {
+                    for (int tt = 0; tt < TTMAX; ++tt) {
                         const int t = 8 * (tt0 + tt) + gq, j = j4 + q;
-                        bf[h][tt][0] = (tok[tt] && j < m) ? (c.U0 ? c.U0[(size_t)t * m + j] : (pUmin[j4] + pUmax[j4]) / 2) : 0.0;
-                    } else if (KIND == K_NEWTON) {
-                        bf[h][tt][0] = c.UC()[idx]; bf[h][tt][NA > 1 ? 1 : 0] = c.HU()[idx];
-                    } else {
-                        bf[h][tt][0] = c.UC()[idx]; bf[h][tt][NA > 1 ? 1 : 0] = c.DU()[idx]; bf[h][tt][NA > 2 ? 2 : 0] = c.HU()[idx];
-                        bf[h][tt][NA > 3 ? 3 : 0] = c.HDU()[idx]; bf[h][tt][NA > 4 ? 4 : 0] = c.DB()[idx];
+                        bf[h][tt] = (tok[tt] && j < m) ? (c.U0 ? c.U0[(size_t)t * m + j] : (pUmin[j4] + pUmax[j4]) / 2) : 0.0;
                     }
                 }
-            }
-        };
-        const int NKP = c.MK / 2;
-        load(cur, 0);
-        for (int kp = 0; kp < NKP; ++kp) {
-            if (kp + 1 < NKP) load(nxt, kp + 1);
+            };
+            const int NKP = c.MK / 2;
+            load(cur, 0);
+            for (int kp = 0; kp < NKP; ++kp) {
+                if (kp + 1 < NKP) load(nxt, kp + 1);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j4 = 8 * kp + 4 * h;
-                double a[TTMAX];
-                double bf[CT];
+                for (int h = 0; h < 2; ++h) {
+                    const int j4 = 8 * kp + 4 * h;
+                    double bf[CT];
 #pragma unroll
-                for (int nt = 0; nt < CT; ++nt) bf[nt] = pB[nt][j4];
-                const double r2 = pR2[j4], rl = pRl[j4];
+                    for (int nt = 0; nt < CT; ++nt) bf[nt] = pB[nt][j4];
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt) {
-                    const int idx = row[tt] + j4;
-                    if (KIND == K_RP) {
-                        a[tt] = cur[h][tt][0];
-                        if (tt < TT) c.UC()[idx] = a[tt];
-                    } else if (KIND == K_NEWTON) {
-                        const double uu = cur[h][tt][0], hh = cur[h][tt][NA > 1 ? 1 : 0];
-                        const double sp = pUmax[j4] - uu, sm = uu - pUmin[j4];
-                        const double dp = rcp_nr(sp), dm = rcp_nr(sm);
-                        const double db = c.kappa * (dp - dm);
-                        const double w = rcp_nr(fma(c.kappa, fma(dp, dp, dm * dm), r2));
-                        const double r = rdu_expr(r2, rl, uu, hh, db);
-                        if (tt < TT) { c.DB()[idx] = db; c.WV()[idx] = w; c.RDU()[idx] = r; }
-                        const double rm = tok[tt] ? r : 0.0;
-                        ss_d = fma(rm, rm, ss_d);
-                        a[tt] = r * w;                                      // p_u = inv(Phi_u) r_du
-                    } else {
-                        const double uv = __fma_rn(ts, cur[h][tt][NA > 1 ? 1 : 0], cur[h][tt][0]);
-                        const double hv = __fma_rn(ts, cur[h][tt][NA > 3 ? 3 : 0], cur[h][tt][NA > 2 ? 2 : 0]);
-                        if (tt < TT) { c.UT()[idx] = uv; c.HUT()[idx] = hv; }
-                        const double r = rdu_expr(r2, rl, uv, hv, cur[h][tt][NA > 4 ? 4 : 0]);
-                        const double rm = tok[tt] ? r : 0.0;
-                        ss_d = fma(rm, rm, ss_d);
-                        a[tt] = uv;
-                    }
+                    for (int tt = 0; tt < TTMAX; ++tt)
+                        if (tt < TT) {
+                            c.UC()[row[tt] + j4] = cur[h][tt];
+#pragma unroll
+                            for (int nt = 0; nt < CT; ++nt) dmma(acc[tt][nt], cur[h][tt], bf[nt]);
+                        }
                 }
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt)
-                    if (tt < TT) {
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int nt = 0; nt < CT; ++nt) dmma(acc[tt][nt], a[tt], bf[nt]);
-                    }
+                    for (int tt = 0; tt < TTMAX; ++tt) cur[h][tt] = nxt[h][tt];
             }
+        } else {
+            // NEWTON: UC, HU in chunks of 2 kk ; TRIAL: UC, DU, HU, HDU, DB in chunks of 1 kk
+            constexpr int CK = (KIND == K_NEWTON) ? 2 : 1, CW = 4 * CK, RS = (CK == 1) ? 4 : 12;
+            const double *arr[NA];
+            if (KIND == K_NEWTON) { arr[0] = c.UC(); arr[NA > 1 ? 1 : 0] = c.HU(); }
+            else { arr[0] = c.UC(); arr[NA > 1 ? 1 : 0] = c.DU(); arr[NA > 2 ? 2 : 0] = c.HU(); arr[NA > 3 ? 3 : 0] = c.HDU(); arr[NA > 4 ? 4 : 0] = c.DB(); }
+            const int nch = c.MK / CK;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int d = 0; d < STREAM_RD; ++d) stream_issue<NA, CW, RS>(c, arr, tt0, TT, d, nch);
+            double *pDB = c.DB(), *pWV = c.WV(), *pRDU = c.RDU(), *pUT = c.UT(), *pHUT = c.HUT();
+            for (int ch = 0; ch < nch; ++ch) {
+                cp_async_wait<STREAM_RD - 1>();
+                __syncwarp();
+                double v[CK][TTMAX][NA];
+                {
+                    const double *slot = c.wsm + (ch % STREAM_RD) * (NA * 8 * TTMAX * RS) + gq * RS + q;
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt)
+                    for (int h = 0; h < CK; ++h)
 #pragma unroll
-                    for (int a = 0; a < NA; ++a) cur[h][tt][a] = nxt[h][tt][a];
+                        for (int tt = 0; tt < TTMAX; ++tt)
+#pragma unroll
+                            for (int a = 0; a < NA; ++a) v[h][tt][a] = (tt < TT) ? slot[(a * 8 * TTMAX + 8 * tt) * RS + 4 * h] : 0.0;
+                }
+                __syncwarp();                                    // the slot is in registers: refill it
+                stream_issue<NA, CW, RS>(c, arr, tt0, TT, ch + STREAM_RD, nch);
+#pragma unroll
+                for (int h = 0; h < CK; ++h) {
+                    const int j4 = CW * ch + 4 * h;
+                    double a[TTMAX];
+                    double bf[CT];
+#pragma unroll
+                    for (int nt = 0; nt < CT; ++nt) bf[nt] = pB[nt][j4];
+                    const double r2 = pR2[j4], rl = pRl[j4];
+#pragma unroll
+                    for (int tt = 0; tt < TTMAX; ++tt) {
+                        const int idx = row[tt] + j4;
+                        if (KIND == K_NEWTON) {
+                            const double uu = v[h][tt][0], hh = v[h][tt][NA > 1 ? 1 : 0];
+                            const double sp = pUmax[j4] - uu, sm = uu - pUmin[j4];
+                            const double dp = rcp_nr(sp), dm = rcp_nr(sm);
+                            const double db = c.kappa * (dp - dm);
+                            const double w = rcp_nr(fma(c.kappa, fma(dp, dp, dm * dm), r2));
+                            const double r = rdu_expr(r2, rl, uu, hh, db);
+                            if (tt < TT) { pDB[idx] = db; pWV[idx] = w; pRDU[idx] = r; }
+                            const double rm = tok[tt] ? r : 0.0;
+                            ss_d = fma(rm, rm, ss_d);
+                            a[tt] = r * w;                                  // p_u = inv(Phi_u) r_du
+                        } else {
+                            const double uv = __fma_rn(ts, v[h][tt][NA > 1 ? 1 : 0], v[h][tt][0]);
+                            const double hv = __fma_rn(ts, v[h][tt][NA > 3 ? 3 : 0], v[h][tt][NA > 2 ? 2 : 0]);
+                            if (tt < TT) { pUT[idx] = uv; pHUT[idx] = hv; }
+                            const double r = rdu_expr(r2, rl, uv, hv, v[h][tt][NA > 4 ? 4 : 0]);
+                            const double rm = tok[tt] ? r : 0.0;
+                            ss_d = fma(rm, rm, ss_d);
+                            a[tt] = uv;
+                        }
+                    }
+#pragma unroll
+                    for (int tt = 0; tt < TTMAX; ++tt)
+                        if (tt < TT) {
+#pragma unroll
+                            for (int nt = 0; nt < CT; ++nt) dmma(acc[tt][nt], a[tt], bf[nt]);
+                        }
+                }
+            }
+            cp_async_wait<0>();
         }
         // ---- x part: A1 v_{t-1} + A2 v_{t-2} (shifted rows read from the scratch arrays, all loads up front) ----
         {
@@ -523,22 +596,29 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c)
 #pragma unroll
                 for (int kk = 0; kk < KS; ++kk) { const double v = pv[4 * kk]; av[tt][kk] = tok[tt] ? v : 0.0; }
             }
-            double2 rc[TTMAX], wc[TTMAX], rn[TTMAX], wn[TTMAX];
-            auto loadrw = [&](double2 (&r)[TTMAX], double2 (&w)[TTMAX], const int jt) {
+            // MODE 1: r_du and w (8 columns per step) come through the cp.async ring
+            const double *arr[2] = {c.RDU(), c.WV()};
+            if (MODE == 1) {
 #pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt) {
-                    const int t = 8 * (tt0 + tt) + gq;
-                    r[tt] = w[tt] = make_double2(0.0, 0.0);
-                    if (MODE == 1 && tok[tt]) {
-                        const size_t idx = (size_t)t * mpad + 8 * jt + 2 * q;
-                        r[tt] = *reinterpret_cast<const double2 *>(c.RDU() + idx);
-                        w[tt] = *reinterpret_cast<const double2 *>(c.WV() + idx);
-                    }
-                }
-            };
-            loadrw(rc, wc, 0);
+                for (int d = 0; d < STREAM_RD; ++d) stream_issue<2, 8, 8>(c, arr, tt0, TT, d, c.MT8);
+            }
             for (int jt = 0; jt < c.MT8; ++jt) {
-                if (jt + 1 < c.MT8) loadrw(rn, wn, jt + 1);
+                double2 rc[TTMAX], wc[TTMAX];
+                if (MODE == 1) {
+                    cp_async_wait<STREAM_RD - 1>();
+                    __syncwarp();
+                    const double *slot = c.wsm + (jt % STREAM_RD) * (2 * 8 * TTMAX * 8) + gq * 8 + 2 * q;
+#pragma unroll
+                    for (int tt = 0; tt < TTMAX; ++tt) {
+                        rc[tt] = wc[tt] = make_double2(0.0, 0.0);
+                        if (tt < TT) {
+                            rc[tt] = *reinterpret_cast<const double2 *>(slot + 8 * tt * 8);
+                            wc[tt] = *reinterpret_cast<const double2 *>(slot + (8 * TTMAX + 8 * tt) * 8);
+                        }
+                    }
+                    __syncwarp();
+                    stream_issue<2, 8, 8>(c, arr, tt0, TT, jt + STREAM_RD, c.MT8);
+                }
                 double acc[TTMAX][2];
 #pragma unroll
                 for (int tt = 0; tt < TTMAX; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
@@ -566,9 +646,8 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c)
                         }
                     }
                 }
-#pragma unroll
-                for (int tt = 0; tt < TTMAX; ++tt) { rc[tt] = rn[tt]; wc[tt] = wn[tt]; }
             }
+            if (MODE == 1) cp_async_wait<0>();
         }
         {   // ---- x part (global loads up front; the epilogue operands two k-steps before the end) ----
             double a1[KS][TTMAX], a2[KS][TTMAX];
@@ -658,29 +737,32 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c)
 // nv columns are pivots; rows below them (e.g. the rhs row) are carried as ordinary rows.
 // On exit d = L (lower triangle; the rest is junk), x = inv(L) (lower triangular).  Returns 0 or failing column + 1.
 // ---------------------------------------------------------------------------------------------
+template <int NVMAX, bool LAST>
 __device__ __forceinline__ int diag8(double (&d)[2], double (&x)[2], const int nv, const int gq, const int q)
 {
     x[0] = (2 * q == gq) ? 1.0 : 0.0;
     x[1] = (2 * q + 1 == gq) ? 1.0 : 0.0;
     int info = 0;
+    // Straight-line code (no warp-divergent control flow around the shuffles): a column >= nv is an identity
+    // column (unit pivot, zero column), for which every update below is an exact no-op.
 #pragma unroll
-    for (int cidx = 0; cidx < 8; ++cidx) {
-        if (cidx < nv) {
-            const int qc = cidx >> 1, ec = cidx & 1;
-            const double p = shfl_d(d[ec], 4 * cidx + qc);              // pivot D[c][c]
-            if (!(p > 0.0) || !(p < 1.0e300)) { if (!info) info = cidx + 1; }
-            const double rs = rsqrt_nr(p);
-            const double mine = d[ec] * rs;                              // column c scaled (held where q == qc)
-            const double lr = shfl_d(mine, 4 * gq + qc);                 // L[gq][c]
-            const double lc0 = shfl_d(mine, 4 * (2 * q) + qc);           // L[2q][c]
-            const double lc1 = shfl_d(mine, 4 * (2 * q + 1) + qc);       // L[2q+1][c]
-            if (q == qc) d[ec] = lr;
-            if (2 * q > cidx) d[0] = fma(-lr, lc0, d[0]);
-            if (2 * q + 1 > cidx) d[1] = fma(-lr, lc1, d[1]);
-            const double e0 = shfl_d(x[0], 4 * cidx + q) * rs, e1 = shfl_d(x[1], 4 * cidx + q) * rs;
-            if (gq == cidx) { x[0] = e0; x[1] = e1; }
-            else if (gq > cidx) { x[0] = fma(-lr, e0, x[0]); x[1] = fma(-lr, e1, x[1]); }
-        }
+    for (int cidx = 0; cidx < NVMAX; ++cidx) {
+        const bool live = LAST ? (cidx < nv) : true;          // only the last diagonal tile can have fewer than 8 pivots
+        const int qc = cidx >> 1, ec = cidx & 1;
+        double p = shfl_d(d[ec], 4 * cidx + qc);                     // pivot D[c][c]
+        p = live ? p : 1.0;
+        if (!(p > 0.0) || !(p < 1.0e300)) { if (!info) info = cidx + 1; }
+        const double rs = rsqrt_nr(p);
+        const double mine = live ? d[ec] * rs : 0.0;                 // column c scaled (held where q == qc)
+        const double lr = shfl_d(mine, 4 * gq + qc);                 // L[gq][c]
+        const double lc0 = shfl_d(mine, 4 * (2 * q) + qc);           // L[2q][c]
+        const double lc1 = shfl_d(mine, 4 * (2 * q + 1) + qc);       // L[2q+1][c]
+        d[ec] = (live && q == qc) ? lr : d[ec];
+        d[0] = (2 * q > cidx) ? fma(-lr, lc0, d[0]) : d[0];
+        d[1] = (2 * q + 1 > cidx) ? fma(-lr, lc1, d[1]) : d[1];
+        const double e0 = shfl_d(x[0], 4 * cidx + q) * rs, e1 = shfl_d(x[1], 4 * cidx + q) * rs;
+        x[0] = (gq == cidx) ? e0 : ((gq > cidx) ? fma(-lr, e0, x[0]) : x[0]);
+        x[1] = (gq == cidx) ? e1 : ((gq > cidx) ? fma(-lr, e1, x[1]) : x[1]);
     }
     return info;
 }
@@ -759,18 +841,31 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
             const double *pB[CT];
 #pragma unroll
             for (int rt = 0; rt < CT; ++rt) pB[rt] = c.sB() + (size_t)(8 * rt + gq) * c.LDB + q;
+            double fr[CT], af[CT];
+#pragma unroll
+            for (int rt = 0; rt < CT; ++rt) fr[rt] = pB[rt][0];
+            {
+                const double wv = wb[0];
+#pragma unroll
+                for (int rt = 0; rt < CT; ++rt) af[rt] = fr[rt] * wv;
+            }
 #pragma unroll 4
             for (int kk = 0; kk < c.MK; ++kk) {
-                const double wv = wb[4 * kk];
-                double fr[CT];
+                // operands of the next step (the last step re-reads its own: harmless)
+                const int kn = (kk + 1 < c.MK) ? kk + 1 : kk;
+                const double wn = wb[4 * kn];
+                double frn[CT], afn[CT];
 #pragma unroll
-                for (int rt = 0; rt < CT; ++rt) fr[rt] = pB[rt][4 * kk];
+                for (int rt = 0; rt < CT; ++rt) frn[rt] = pB[rt][4 * kn];
+#pragma unroll
+                for (int rt = 0; rt < CT; ++rt) afn[rt] = frn[rt] * wn;
 #pragma unroll
                 for (int rt = 0; rt < CT; ++rt) {
-                    const double a = fr[rt] * wv;
 #pragma unroll
-                    for (int ct = 0; ct <= rt; ++ct) dmma(sacc[rt][ct], a, fr[ct]);
+                    for (int ct = 0; ct <= rt; ++ct) dmma(sacc[rt][ct], af[rt], fr[ct]);
                 }
+#pragma unroll
+                for (int rt = 0; rt < CT; ++rt) { fr[rt] = frn[rt]; af[rt] = afn[rt]; }
             }
         }
         {   // + iterate-independent part of Y[i,i]; rhs row <- -beta_i
@@ -817,7 +912,40 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
         }
         PROF_T(8);
         // ================= phase B: L_i and inv(L_i) on the accumulator tiles =================
-        // the iterate-independent part of Y[i+1,i] is requested now and consumed in phase C
+        double linv[CT][CT][2];                              // inv(L_i) tiles (rt, ct <= rt)
+        int info = 0;
+#pragma unroll
+        for (int kb = 0; kb < CT; ++kb) {
+            const int nv = min(8, n - 8 * kb);
+            if (nv < 8) {                                    // columns >= n of the last diagonal tile: identity
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int cg = 2 * q + e;
+                    if (cg >= nv) sacc[kb][kb][e] = (gq == cg) ? 1.0 : 0.0;
+                }
+            }
+            // columns of this tile that can be pivots: 8, except NPOT - 8 (CT - 1) for the last tile
+            const int inf = (kb < CT - 1) ? diag8<8, false>(sacc[kb][kb], linv[kb][kb], nv, gq, q)
+                                          : diag8<NPOT - 8 * (CT - 1), true>(sacc[kb][kb], linv[kb][kb], nv, gq, q);
+            if (inf && !info) info = 8 * kb + inf;
+            if (nv < 8 && gq >= nv) { linv[kb][kb][0] = 0.0; linv[kb][kb][1] = 0.0; }
+#pragma unroll
+            for (int rt = kb + 1; rt < RT; ++rt) {           // panel: L[rt][kb] = S[rt][kb] inv(L_kk)'
+                double o[2] = {0.0, 0.0};
+                mma_xt(o, sacc[rt][kb], linv[kb][kb]);
+                sacc[rt][kb][0] = o[0]; sacc[rt][kb][1] = o[1];
+            }
+#pragma unroll
+            for (int rt = kb + 1; rt < RT; ++rt) {           // trailing update
+                const double nx[2] = {dneg(sacc[rt][kb][0]), dneg(sacc[rt][kb][1])};
+#pragma unroll
+                for (int ct = kb + 1; ct < CT; ++ct)
+                    if (ct <= rt) mma_xt(sacc[rt][ct], nx, sacc[ct][kb]);
+            }
+        }
+        if (info) return i + 1;
+        // the iterate-independent part of Y[i+1,i]: requested here (the diagonal blocks are done, registers are free again),
+        // consumed in phase C after the triangular inverse
         double macc[CT][CT][2];
         {
             const int y1 = c.y1i[i];
@@ -836,36 +964,6 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
                 }
             }
         }
-        double linv[CT][CT][2];                              // inv(L_i) tiles (rt, ct <= rt)
-        int info = 0;
-#pragma unroll
-        for (int kb = 0; kb < CT; ++kb) {
-            const int nv = min(8, n - 8 * kb);
-            if (nv < 8) {                                    // columns >= n of the last diagonal tile: identity
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int cg = 2 * q + e;
-                    if (cg >= nv) sacc[kb][kb][e] = (gq == cg) ? 1.0 : 0.0;
-                }
-            }
-            const int inf = diag8(sacc[kb][kb], linv[kb][kb], nv, gq, q);
-            if (inf && !info) info = 8 * kb + inf;
-            if (nv < 8 && gq >= nv) { linv[kb][kb][0] = 0.0; linv[kb][kb][1] = 0.0; }
-#pragma unroll
-            for (int rt = kb + 1; rt < RT; ++rt) {           // panel: L[rt][kb] = S[rt][kb] inv(L_kk)'
-                double o[2] = {0.0, 0.0};
-                mma_xt(o, sacc[rt][kb], linv[kb][kb]);
-                sacc[rt][kb][0] = o[0]; sacc[rt][kb][1] = o[1];
-            }
-#pragma unroll
-            for (int rt = kb + 1; rt < RT; ++rt) {           // trailing update
-                const double nx[2] = {dneg(sacc[rt][kb][0]), dneg(sacc[rt][kb][1])};
-#pragma unroll
-                for (int ct = kb + 1; ct < CT; ++ct)
-                    if (ct <= rt) mma_xt(sacc[rt][ct], nx, sacc[ct][kb]);
-            }
-        }
-        if (info) return i + 1;
         {   // inv(L) off-diagonal tiles, row by row from the diagonal leftwards:
             //   inv(L)[rt][ct] = -(sum_{j=ct+1..rt} inv(L)[rt][j] L[j][ct]) inv(L_ct,ct)
             double lt[CT][CT][2], xdt[CT][2];
