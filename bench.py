@@ -281,7 +281,8 @@ def main():
             "e2e": {"value": solves / e2e_s_max, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "fmpc_step (C-ABI, pinned host buffers)"},
             "gpu_launches": launches_all,
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)", "kernel": "fmpc_solve_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)",
+                         "kernel": {2: "fmpc_solve_kernel_warp<28,4>", 1: "fmpc_solve_kernel_mma<28>", 0: "fmpc_solve_kernel_v1"}.get(hb.kernel_kind, "?"), "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "measured live: fmpc_fp64_peak DMMA m8n8k4 %.2f / DFMA %.2f TFLOP/s "
                                         "(MEASURED_PEAKS.json has no FP64 entry)" % (peak_dmma, peak_dfma),

@@ -155,7 +155,7 @@ struct WGeom {
         g.const_doubles = (g.const_doubles + 1) & ~(size_t)1;
         g.warp_doubles = 3 * (size_t)g.BLK + (size_t)g.WB;
         if (g.warp_doubles < 3 * (size_t)g.NN + 128) g.warp_doubles = 3 * (size_t)g.NN + 128;   // backward ring: 3 slots of NN + vectors
-        if (g.warp_doubles < 2304) g.warp_doubles = 2304;                                   // u-space stream ring of the passes (4 slots)
+        if (g.warp_doubles < 2400) g.warp_doubles = 2400;                                   // u-space stream ring of the passes
         g.tail_doubles = 8 * (size_t)g.LD + 8;   // overrun reads of the last rows stay inside the allocation
         return g;
     }
@@ -248,20 +248,41 @@ enum { K_RP = 0, K_NEWTON = 1, K_TRIAL = 2 };
 // Slot layout [array][row 0..23][RS], RS chosen so that the fragment reads are conflict-free.
 // ---------------------------------------------------------------------------------------------
 constexpr int STREAM_RD = 4;
-template <int NA, int CW, int RS>
-__device__ __forceinline__ void stream_issue(const WCtx &c, const double *const (&arr)[NA], const int tt0, const int TT, const int ch, const int nch)
+__device__ __forceinline__ void cp_async16_s(const unsigned saddr, const double *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+// per-lane piece table of one chunk shape (fixed over the chunks of a pass): 16-byte piece p = lane + 32 it covers
+// row p / PPR, columns 2 (p % PPR) .. +1 of the chunk
+template <int CW> struct StreamIdx {
+    static constexpr int PPR = CW / 2, NIT = (8 * TTMAX * PPR + 31) / 32;
+    int soff[NIT];
+    unsigned doff[NIT];
+    bool ok[NIT];
+};
+template <int CW, int RS>
+__device__ __forceinline__ void stream_setup(StreamIdx<CW> &si, const WCtx &c, const int TT)
+{
+#pragma unroll
+    for (int it = 0; it < StreamIdx<CW>::NIT; ++it) {
+        const int p = c.lane + 32 * it, row = p / StreamIdx<CW>::PPR, pc = p - row * StreamIdx<CW>::PPR;
+        si.ok[it] = p < 8 * TT * StreamIdx<CW>::PPR;
+        si.soff[it] = row * c.mpad + 2 * pc;
+        si.doff[it] = (unsigned)((row * RS + 2 * pc) * 8);
+    }
+}
+template <int NA, int CW, int RS, int RD>
+__device__ __forceinline__ void stream_issue(const WCtx &c, const StreamIdx<CW> &si, const double *const (&arr)[NA], const unsigned sbase,
+                                             const int tt0, const int ch, const int nch)
 {
     if (ch < nch) {
-        double *slot = c.wsm + (ch % STREAM_RD) * (NA * 8 * TTMAX * RS);
-        const int rows = 8 * TT;
+        const unsigned sl = sbase + (unsigned)(ch % RD) * (unsigned)(NA * 8 * TTMAX * RS * 8);
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
             const double *src = arr[a] + (size_t)(8 * tt0) * c.mpad + CW * ch;
-            double *dst = slot + a * (8 * TTMAX * RS);
-            for (int p = c.lane; p < rows * (CW / 2); p += 32) {
-                const int row = p / (CW / 2), pc = p - row * (CW / 2);
-                cp_async16(dst + row * RS + 2 * pc, src + (size_t)row * c.mpad + 2 * pc);
-            }
+#pragma unroll
+            for (int it = 0; it < StreamIdx<CW>::NIT; ++it)
+                if (si.ok[it]) cp_async16_s(sl + (unsigned)(a * 8 * TTMAX * RS * 8) + si.doff[it], src + si.soff[it]);
         }
     }
     cp_async_commit();
@@ -405,19 +426,23 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
         } else {
             // NEWTON: UC, HU in chunks of 2 kk ; TRIAL: UC, DU, HU, HDU, DB in chunks of 1 kk
             constexpr int CK = (KIND == K_NEWTON) ? 2 : 1, CW = 4 * CK, RS = (CK == 1) ? 4 : 12;
+            constexpr int RD = (NA * 8 * TTMAX * RS * 5 <= 2400) ? 5 : 4;         // ring depth: what fits the guaranteed 2400 doubles
             const double *arr[NA];
             if (KIND == K_NEWTON) { arr[0] = c.UC(); arr[NA > 1 ? 1 : 0] = c.HU(); }
             else { arr[0] = c.UC(); arr[NA > 1 ? 1 : 0] = c.DU(); arr[NA > 2 ? 2 : 0] = c.HU(); arr[NA > 3 ? 3 : 0] = c.HDU(); arr[NA > 4 ? 4 : 0] = c.DB(); }
             const int nch = c.MK / CK;
+            StreamIdx<CW> si;
+            stream_setup<CW, RS>(si, c, TT);
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(c.wsm);
 #pragma unroll
-            for (int d = 0; d < STREAM_RD; ++d) stream_issue<NA, CW, RS>(c, arr, tt0, TT, d, nch);
+            for (int d = 0; d < RD; ++d) stream_issue<NA, CW, RS, RD>(c, si, arr, sbase, tt0, d, nch);
             double *pDB = c.DB(), *pWV = c.WV(), *pRDU = c.RDU(), *pUT = c.UT(), *pHUT = c.HUT();
             for (int ch = 0; ch < nch; ++ch) {
-                cp_async_wait<STREAM_RD - 1>();
+                cp_async_wait<RD - 1>();
                 __syncwarp();
                 double v[CK][TTMAX][NA];
                 {
-                    const double *slot = c.wsm + (ch % STREAM_RD) * (NA * 8 * TTMAX * RS) + gq * RS + q;
+                    const double *slot = c.wsm + (ch % RD) * (NA * 8 * TTMAX * RS) + gq * RS + q;
 #pragma unroll
                     for (int h = 0; h < CK; ++h)
 #pragma unroll
@@ -426,7 +451,7 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
                             for (int a = 0; a < NA; ++a) v[h][tt][a] = (tt < TT) ? slot[(a * 8 * TTMAX + 8 * tt) * RS + 4 * h] : 0.0;
                 }
                 __syncwarp();                                    // the slot is in registers: refill it
-                stream_issue<NA, CW, RS>(c, arr, tt0, TT, ch + STREAM_RD, nch);
+                stream_issue<NA, CW, RS, RD>(c, si, arr, sbase, tt0, ch + RD, nch);
 #pragma unroll
                 for (int h = 0; h < CK; ++h) {
                     const int j4 = CW * ch + 4 * h;
@@ -598,9 +623,12 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c)
             }
             // MODE 1: r_du and w (8 columns per step) come through the cp.async ring
             const double *arr[2] = {c.RDU(), c.WV()};
+            StreamIdx<8> si;
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(c.wsm);
             if (MODE == 1) {
+                stream_setup<8, 8>(si, c, TT);
 #pragma unroll
-                for (int d = 0; d < STREAM_RD; ++d) stream_issue<2, 8, 8>(c, arr, tt0, TT, d, c.MT8);
+                for (int d = 0; d < STREAM_RD; ++d) stream_issue<2, 8, 8, STREAM_RD>(c, si, arr, sbase, tt0, d, c.MT8);
             }
             for (int jt = 0; jt < c.MT8; ++jt) {
                 double2 rc[TTMAX], wc[TTMAX];
@@ -617,7 +645,7 @@ __device__ __forceinline__ void pass_Ct(const WCtx &c)
                         }
                     }
                     __syncwarp();
-                    stream_issue<2, 8, 8>(c, arr, tt0, TT, jt + STREAM_RD, c.MT8);
+                    stream_issue<2, 8, 8, STREAM_RD>(c, si, arr, sbase, tt0, jt + STREAM_RD, c.MT8);
                 }
                 double acc[TTMAX][2];
 #pragma unroll
@@ -1329,22 +1357,25 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
             ++iters;
         }
         __syncwarp();
-        {   // iterate -> outputs (8 elements in flight per lane)
+        {   // iterate -> outputs: rows of the padded scratch arrays to the dense output rows, 4 rows in flight per lane
             double *uo = A.U + (size_t)b * m * T, *xo = A.X + (size_t)b * n * T;
             const double *pu = c.UC(), *px = c.XC();
-            for (int e0 = lane; e0 < T * m; e0 += 256) {
-                double v[8];
+            for (int j0 = 0; j0 < m; j0 += 32) {
+                const int j = j0 + lane;
+                for (int t0 = 0; t0 < T; t0 += 4) {
+                    double v[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; v[u] = 0.0; if (e < T * m) { const int t = e / m, j = e - t * m; v[u] = pu[(size_t)t * mpad + j]; } }
+                    for (int u = 0; u < 4; ++u) v[u] = (j < m && t0 + u < T) ? pu[(size_t)(t0 + u) * mpad + j] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < T * m) uo[e] = v[u]; }
+                    for (int u = 0; u < 4; ++u) if (j < m && t0 + u < T) uo[(size_t)(t0 + u) * m + j] = v[u];
+                }
             }
-            for (int e0 = lane; e0 < T * n; e0 += 256) {
+            for (int t0 = 0; t0 < T; t0 += 8) {
                 double v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; v[u] = 0.0; if (e < T * n) { const int t = e / n, k = e - t * n; v[u] = px[(size_t)t * npad + k]; } }
+                for (int u = 0; u < 8; ++u) v[u] = (lane < n && t0 + u < T) ? px[(size_t)(t0 + u) * npad + lane] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int e = e0 + 32 * u; if (e < T * n) xo[e] = v[u]; }
+                for (int u = 0; u < 8; ++u) if (lane < n && t0 + u < T) xo[(size_t)(t0 + u) * n + lane] = v[u];
             }
         }
         if (lane == 0) {
@@ -1369,7 +1400,10 @@ static int config_warp(const WGeom &G, SolveLaunchCfg *cfg, const cudaDeviceProp
     if (G.smem_doubles(1) * 8 > avail) return -3;
     int warps = 8;
     while (warps > 1 && G.smem_doubles(warps) * 8 > avail) --warps;
-    if (const char *e = getenv("FMPC_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 1 && v < warps) warps = v; }
+    // measured on B200 (profiles/r01_v3_warp_sweep.log): filling the last ~16 KB of the unified L1/shared array with an
+    // eighth warp costs more (no L1 left for the constant pool and the scratch streams) than the extra instance gains
+    if (warps == 8 && G.smem_doubles(warps) * 8 + 16384 > avail) warps = 7;
+    if (const char *e = getenv("FMPC_WARPS_PER_CTA")) { const int v = atoi(e); if (v >= 1 && G.smem_doubles(v) * 8 <= avail && v <= 8) warps = v; }
     const size_t smem = G.smem_doubles(warps) * 8;
     if (cudaFuncSetAttribute(fmpc_solve_kernel_warp<NPOT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
     cfg->grid = prop.multiProcessorCount;

@@ -46,6 +46,16 @@ SMALL = [
     dict(seed=10, n=27, m=144, T=10, nb=4, umax=3.0, a2=False, warm=True),   # C1 shape, VAR(1)
     dict(seed=11, n=28, m=144, T=20, nb=6, umax=0.5, warm=True),      # C2 shape, active barrier
     dict(seed=12, n=66, m=144, T=30, nb=2, umax=1.0, warm=True),      # C5 shape
+    # every instantiation of the warp-per-instance kernel (block size classes 8/16/24/28/32, with and without a
+    # spare padding row for the forward-substitution row), odd m, T across 8-stage tile boundaries
+    dict(seed=13, n=12, m=9, T=7, nb=3, umax=0.4, warm=True),
+    dict(seed=14, n=16, m=11, T=9, nb=3, umax=0.4, warm=True, xf=True),
+    dict(seed=15, n=20, m=17, T=26, nb=3, umax=0.4, warm=True),
+    dict(seed=16, n=24, m=8, T=4, nb=2, umax=0.4, warm=True),
+    dict(seed=17, n=30, m=33, T=5, nb=2, umax=0.4, warm=True),
+    dict(seed=18, n=32, m=16, T=5, nb=2, umax=0.4, warm=True, xf=True),
+    dict(seed=19, n=28, m=144, T=20, nb=40, umax=0.5, warm=True, xf=True),   # more instances than one CTA holds
+    dict(seed=20, n=8, m=6, T=17, nb=9, umax=0.3, a2=False, xf=True, warm=True),
 ]
 
 
@@ -66,6 +76,15 @@ def test_parity_vs_golden(pk, path):
     assert_parity(out, c, c["nb"])
     assert np.array_equal(out["iters"], c["iters"])
     assert np.array_equal(out["status"] == 1, c["early_exit"])
+
+
+def test_kernel_selection(pk):
+    """n <= 32 runs on the warp-per-instance DMMA kernel, larger n on the generic kernel (never a CPU path)."""
+    for n, kind in ((6, 2), (28, 2), (32, 2), (33, 0)):
+        c = small_problem(1, n, 4, 3, 1, 1.0)
+        hb = make_handle(pk, c)
+        assert hb.kernel_kind == kind
+        hb.close()
 
 
 def test_line_search_both_regimes(pk, fref):
