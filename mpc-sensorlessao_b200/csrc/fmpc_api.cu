@@ -84,6 +84,10 @@ struct fmpc_handle {
     SolveLaunchCfg cfg{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host-buffer entry points: copy-in / solve / copy-out of successive instance chunks overlap on three streams
+    static constexpr int MAX_CHUNKS = 8;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     std::vector<void *> sys_allocs;       // problem-constant device arrays
     DevBuf ws, counters;                  // per-CTA scratch; {counter u32 (pad), iters_total u64}
     // staging for the host-pointer entry points
@@ -276,6 +280,9 @@ void fmpc_destroy(fmpc_handle *h)
     for (DevBuf *b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < fmpc_handle::MAX_CHUNKS; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -371,6 +378,11 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     }
     if (ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
     if (ok && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) ok = false;
+    if (ok && (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+               cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess)) ok = false;
+    for (int i = 0; ok && i < fmpc_handle::MAX_CHUNKS; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
     if (!ok) { fmpc_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
     return FMPC_OK;
@@ -411,7 +423,7 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
 
 static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
                        const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
-                       double *X, double *U, int *status, int *iters, cudaStream_t st)
+                       double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false)
 {
     StepArgs A{};
     A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
@@ -423,7 +435,7 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     A.prof = (long long *)(h->counters.as<char>() + 64);
-    CU_OK(cudaMemsetAsync(h->counters.p, 0, 256, st));
+    CU_OK(cudaMemsetAsync(h->counters.p, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
     if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, h->cfg, st);
     else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
     else fmpc_launch_solve(h->S, A, h->cfg, st);
@@ -477,27 +489,55 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
         for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
         nu_src = h->h_nu.data();
     }
-    CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, st));
-    if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, st));
-    if (w) CU_OK(cudaMemcpyAsync(h->d_w.p, w, nb * T * n * 8, cudaMemcpyHostToDevice, st));
-    if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.p, xf, nb * n * 8, cudaMemcpyHostToDevice, st));
-    if (X0) {
-        CU_OK(cudaMemcpyAsync(h->d_X.p, X0, nb * n * T * 8, cudaMemcpyHostToDevice, st));
-        CU_OK(cudaMemcpyAsync(h->d_U.p, U0, nb * m * T * 8, cudaMemcpyHostToDevice, st));
+    // Instances are independent: the batch is cut into chunks of about one launch wave each, and copy-in (s_in),
+    // solve (st) and copy-out (s_out) of successive chunks overlap.  With pageable host memory the copies degrade to
+    // staged synchronous ones; the results are the same.
+    int nch = (int)((nb + (size_t)h->cfg.slots / 2) / (size_t)h->cfg.slots);
+    if (nch < 1) nch = 1;
+    if (nch > fmpc_handle::MAX_CHUNKS) nch = fmpc_handle::MAX_CHUNKS;
+    const size_t per = (nb + nch - 1) / nch;
+    cudaStream_t si = h->s_in, so = h->s_out;
+    const size_t Tn = (size_t)T * n, Tm = (size_t)T * m;
+    while (nch > 1 && (size_t)(nch - 1) * per >= nb) --nch;           // no empty trailing chunk
+    // enqueue order per chunk: copy-in(ci), solve(ci), copy-out(ci-1) -- so that even blocking (pageable) copies
+    // leave the solve of the current chunk running underneath them
+    for (int ci = 0; ci <= nch; ++ci) {
+        if (ci < nch) {
+            const size_t b0 = (size_t)ci * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
+            CU_OK(cudaMemcpyAsync(h->d_x0.as<double>() + b0 * n, x0 + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
+            if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.as<double>() + b0 * n, x0_pre + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
+            if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, w + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
+            if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.as<double>() + b0 * n, xf + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
+            if (X0) {
+                CU_OK(cudaMemcpyAsync(h->d_X.as<double>() + b0 * Tn, X0 + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
+                CU_OK(cudaMemcpyAsync(h->d_U.as<double>() + b0 * Tm, U0 + b0 * Tm, cb * Tm * 8, cudaMemcpyHostToDevice, si));
+            }
+            CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + b0 * NBn, nu_src + b0 * NBn, cb * NBn * 8, cudaMemcpyHostToDevice, si));
+            CU_OK(cudaEventRecord(h->ev_in[ci], si));
+            CU_OK(cudaStreamWaitEvent(st, h->ev_in[ci], 0));
+            if (ci == 0) CU_OK(cudaEventRecord(h->ev0, st));
+            rc = step_device(h, p, (int)cb, h->d_x0.as<double>() + b0 * n, x0_pre ? h->d_x0pre.as<double>() + b0 * n : nullptr,
+                             w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
+                             X0 ? h->d_X.as<double>() + b0 * Tn : nullptr, X0 ? h->d_U.as<double>() + b0 * Tm : nullptr,
+                             h->d_nu0.as<double>() + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
+                             h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, st, ci > 0);
+            if (rc) return rc;
+            CU_OK(cudaEventRecord(h->ev_k[ci], st));
+            if (ci == nch - 1) CU_OK(cudaEventRecord(h->ev1, st));
+        }
+        if (ci >= 1) {
+            const int cj = ci - 1;
+            const size_t b0 = (size_t)cj * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
+            CU_OK(cudaStreamWaitEvent(so, h->ev_k[cj], 0));
+            CU_OK(cudaMemcpyAsync(X + b0 * Tn, h->d_X.as<double>() + b0 * Tn, cb * Tn * 8, cudaMemcpyDeviceToHost, so));
+            CU_OK(cudaMemcpyAsync(U + b0 * Tm, h->d_U.as<double>() + b0 * Tm, cb * Tm * 8, cudaMemcpyDeviceToHost, so));
+            if (status) CU_OK(cudaMemcpyAsync(status + b0, h->d_status.as<int>() + b0, cb * 4, cudaMemcpyDeviceToHost, so));
+            if (iters) CU_OK(cudaMemcpyAsync(iters + b0, h->d_iters.as<int>() + b0, cb * 4, cudaMemcpyDeviceToHost, so));
+        }
     }
-    CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, st));
-    CU_OK(cudaEventRecord(h->ev0, st));
-    rc = step_device(h, p, nbatch, h->d_x0.as<double>(), x0_pre ? h->d_x0pre.as<double>() : nullptr,
-                     w ? h->d_w.as<double>() : nullptr, xf ? h->d_xf.as<double>() : nullptr,
-                     X0 ? h->d_X.as<double>() : nullptr, X0 ? h->d_U.as<double>() : nullptr, h->d_nu0.as<double>(),
-                     h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
-    if (rc) return rc;
-    CU_OK(cudaEventRecord(h->ev1, st));
-    CU_OK(cudaMemcpyAsync(X, h->d_X.p, nb * n * T * 8, cudaMemcpyDeviceToHost, st));
-    CU_OK(cudaMemcpyAsync(U, h->d_U.p, nb * m * T * 8, cudaMemcpyDeviceToHost, st));
-    if (status) CU_OK(cudaMemcpyAsync(status, h->d_status.p, nb * 4, cudaMemcpyDeviceToHost, st));
-    if (iters) CU_OK(cudaMemcpyAsync(iters, h->d_iters.p, nb * 4, cudaMemcpyDeviceToHost, st));
+    CU_OK(cudaStreamSynchronize(so));
     CU_OK(cudaStreamSynchronize(st));
+    CU_OK(cudaStreamSynchronize(si));
     if (telapsed) { float ms = 0.f; CU_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *telapsed = ms * 1e-3; }
     return FMPC_OK;
 }
