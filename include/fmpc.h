@@ -46,7 +46,7 @@ enum {
     FMPC_ERR_B_SIZE         = -11,  /* fast_mpc_eq_const.m:31-32   'The equality control dynamics matrix size does not match' */
     FMPC_ERR_INIT_SIZE      = -12,  /* fast_mpc_init.m:13-14       'Initialization size mismatch (T*(n+m))' */
     FMPC_ERR_NOT_PD         = -13,  /* chol() failure on a problem-constant block (Q, Qf, R) */
-    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover yet */
+    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover (non-diagonal R) */
     FMPC_ERR_BATCH          = -15,  /* nbatch > max_batch of the handle */
     FMPC_ERR_CUDA           = -16,  /* no usable sm_100 device / CUDA runtime error (no CPU fallback) */
     FMPC_ERR_PARAM          = -17   /* kappa <= 0, niters < 0, beta not in (0,1) ... */
@@ -77,7 +77,10 @@ typedef struct fmpc_sys {
     const double *x_min, *x_max;    /* n; used for the cold-start midpoint only (fast_mpc_init.m:19) */
     const double *u_min, *u_max;    /* m; box rows fast_mpc_ineq_const.m:42-56 */
     const double *du_min, *du_max;  /* m; VAR_1 ramp rows (VAR_1/fast_mpc_ineq_const.m:58-79); may be NULL if !ramp_rows */
-    int ramp_rows;          /* 0: box only (VAR_2 semantics); 1: VAR_1 ramp rows */
+    int ramp_rows;          /* 0: box only (VAR_2 semantics); 1: VAR_1 ramp rows (needs u_prev at every step) */
+    int var1_literal_bug;   /* var_order == 1 only.  1: write the second block row of C at columns n : 3n+m-1 exactly as
+                             * VAR_1/fast_mpc_eq_const.m:34-37 does -- bit-for-bit the reference's VAR_1;
+                             * 0: the corrected placement m+1 : 2(n+m) (= VAR_2 code with A2 = 0) */
 } fmpc_sys;
 
 /* Solver parameters: arguments (nw, k) of mpc_fixed_log_newton (VAR_2/Fast_MPC2.m:124) plus the
@@ -190,7 +193,8 @@ long long fmpc_launch_count(const fmpc_handle *h);
  * requires a device sync, so call it outside timed regions. */
 long long fmpc_last_newton_iters(fmpc_handle *h);
 /* Which solve kernel the handle selected: 2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA-per-instance
- * DMMA kernel (experiments), 0 = generic kernel (any n). */
+ * DMMA kernel (experiments), 0 = generic kernel (any n), 3 = general-structure kernel (VAR_1 ramp rows, literal
+ * VAR_1 columns, dense Q / Qf). */
 int fmpc_kernel_kind(const fmpc_handle *h);
 /* Phase cycle counters of the last solve launch, summed over warps (all zero unless the library was
  * built with -DFMPC_PROF): init, newton pass, forward sweep, backward sweep, C' pass, line search,

@@ -23,7 +23,7 @@ class FmpcSys(C.Structure):
     _fields_ = [("n", C.c_int), ("m", C.c_int), ("T", C.c_int), ("var_order", C.c_int),
                 ("A1", dp), ("A2", dp), ("B", dp), ("Q", dp), ("R", dp), ("Qf", dp),
                 ("q", dp), ("r", dp), ("qf", dp), ("x_min", dp), ("x_max", dp), ("u_min", dp), ("u_max", dp),
-                ("du_min", dp), ("du_max", dp), ("ramp_rows", C.c_int)]
+                ("du_min", dp), ("du_max", dp), ("ramp_rows", C.c_int), ("var1_literal_bug", C.c_int)]
 
 
 class FmpcParams(C.Structure):

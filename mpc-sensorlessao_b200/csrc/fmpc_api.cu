@@ -81,6 +81,8 @@ struct fmpc_handle {
     int device = 0;
     int n = 0, m = 0, T = 0, var_order = 2, max_batch = 0;
     DevSys S{};
+    GenSys G{};
+    int ramp = 0;
     SolveLaunchCfg cfg{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -262,7 +264,7 @@ const char *fmpc_strerror(int code)
     case FMPC_ERR_B_SIZE: return "The equality control dynamics matrix size does not match";
     case FMPC_ERR_INIT_SIZE: return "Initialization size mismatch (T*(n+m))";
     case FMPC_ERR_NOT_PD: return "cost matrix is not positive definite";
-    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (dense Q/R or VAR_1 ramp rows; see DESIGN.md)";
+    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (non-diagonal R, or a literal VAR_1 C that MATLAB itself would reject; see DESIGN.md)";
     case FMPC_ERR_BATCH: return "nbatch exceeds the handle's max_batch";
     case FMPC_ERR_CUDA: return "no usable sm_100 CUDA device or CUDA runtime error (there is no CPU fallback)";
     case FMPC_ERR_PARAM: return "invalid solver parameter";
@@ -295,8 +297,11 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     if (rc) return rc;
     if (max_batch < 1) return FMPC_ERR_DIM;
     const int n = s->n, m = s->m, T = s->T;
-    if (!is_diag(s->Q, n) || !is_diag(s->Qf, n) || !is_diag(s->R, m)) return FMPC_ERR_UNSUPPORTED;
-    if (s->ramp_rows) return FMPC_ERR_UNSUPPORTED;
+    if (!is_diag(s->R, m)) return FMPC_ERR_UNSUPPORTED;      // dense R: Phi_uu loses its per-actuator structure
+    // general-structure kernel: VAR_1 ramp rows, the literal VAR_1 column placement, dense Q / Qf
+    const bool lit = (s->var_order == 1) && s->var1_literal_bug;
+    const bool need_gen = s->ramp_rows || lit || !is_diag(s->Q, n) || !is_diag(s->Qf, n);
+    if (lit && T < 3) return FMPC_ERR_UNSUPPORTED;           // fast_mpc_eq_const.m:55 then rewrites the mis-placed row itself
     for (int k = 0; k < n; ++k)
         if (!(s->Q[(size_t)k * n + k] > 0.0) || !(s->Qf[(size_t)k * n + k] > 0.0)) return FMPC_ERR_NOT_PD;
     for (int j = 0; j < m; ++j)
@@ -307,6 +312,7 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     fmpc_handle *h = new (std::nothrow) fmpc_handle();
     if (!h) return FMPC_ERR_CUDA;
     h->device = device; h->n = n; h->m = m; h->T = T; h->var_order = s->var_order; h->max_batch = max_batch;
+    h->ramp = s->ramp_rows ? 1 : 0;
     const bool a2 = (s->var_order == 2);
 
     std::vector<double> B(s->B, s->B + (size_t)n * m), Bt((size_t)n * m);
@@ -323,7 +329,8 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
         if (s->qf) qfl[k] = s->qf[k];
     }
     YTables Y;
-    build_y_tables(s, qi, qif, Y);
+    if (!need_gen) build_y_tables(s, qi, qif, Y);
+    else { Y.pool.assign((size_t)n * n, 0.0); Y.ydi.assign(T + 1, -1); Y.y1i.assign(T + 1, -1); Y.y2i.assign(T + 1, -1); }
 
     DevSys &S = h->S;
     S.n = n; S.m = m; S.T = T; S.has_a2 = a2 ? 1 : 0;
@@ -334,7 +341,8 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     std::vector<double> umin(s->u_min, s->u_min + m), umax(s->u_max, s->u_max + m), xmin(s->x_min, s->x_min + n), xmax(s->x_max, s->x_max + n);
     UP(umin, umin); UP(umax, umax); UP(xmin, xmin); UP(xmax, xmax);
     UP(ypool, Y.pool); UP(ydi, Y.ydi); UP(y1i, Y.y1i); UP(y2i, Y.y2i);
-    {   // pair-product matrix for the DMMA path
+    if (need_gen) { S.G = nullptr; S.ypk = nullptr; S.npairs = S.Mp = S.mp = 0; }
+    else {   // pair-product matrix for the DMMA path
         const int np = n * (n + 1) / 2, Mp = (np + 7) & ~7, mp = (m + 3) & ~3;
         std::vector<double> G((size_t)Mp * mp, 0.0);
         for (int r = 0; r < n; ++r)
@@ -352,7 +360,11 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
         UP(ypk, ypk);
     }
 #undef UP
-    if (ok) {
+    if (ok && need_gen) {
+        const int rcg = fmpc_gen_create(s, device, &h->G, h->sys_allocs, &h->cfg);
+        if (rcg != FMPC_OK) { fmpc_destroy(h); return rcg; }
+        if (h->cfg.slots > max_batch) h->cfg.slots = max_batch;
+    } else if (ok) {
         // kernel selection: warp-per-instance DMMA kernel (n <= 32) > CTA DMMA kernel (experiments only) > generic
         const char *force = getenv("FMPC_FORCE_KERNEL");       // "v1" | "v2" : A/B experiments
         const bool want_v1 = force && force[0] == 'v' && force[1] == '1';
@@ -422,21 +434,24 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
 }
 
 static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
-                       const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
+                       const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
                        double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false)
 {
     StepArgs A{};
     A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
     A.kappa = p->kappa; A.niters = p->niters; A.ls_max = p->ls_max;
     A.alpha = p->alpha; A.beta = p->beta; A.tol_r = p->tol_r; A.tol_p = p->tol_p;
-    A.x0 = x0; A.x0_pre = x0_pre; A.w = w; A.xf = xf; A.X0 = X0; A.U0 = U0; A.nu0 = nu0;
+    A.x0 = x0; A.x0_pre = x0_pre; A.u_prev = u_prev; A.w = w; A.xf = xf; A.X0 = X0; A.U0 = U0; A.nu0 = nu0;
     A.X = X; A.U = U; A.status = status; A.iters = iters;
     A.counter = h->counters.as<unsigned int>();
     A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     A.prof = (long long *)(h->counters.as<char>() + 64);
     CU_OK(cudaMemsetAsync(h->counters.p, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
-    if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, h->cfg, st);
+    if (h->cfg.use_mma == 3) {
+        if (nbatch > h->max_batch) return FMPC_ERR_BATCH;     // its scratch is sized by max_batch
+        fmpc_launch_solve_gen(h->S, h->G, A, h->cfg, st);
+    } else if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, h->cfg, st);
     else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
     else fmpc_launch_solve(h->S, A, h->cfg, st);
     CU_OK(cudaGetLastError());
@@ -448,8 +463,8 @@ int fmpc_step_d(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *
                 const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0,
                 const double *nu0, double *X, double *U, int *status, int *iters, void *stream)
 {
-    (void)u_prev;
     if (!h || !x0 || !X || !U || !nu0) return FMPC_ERR_NULL;
+    if (h->ramp && !u_prev) return FMPC_ERR_U_BOUND_SIZE;
     int rc = validate_params(p);
     if (rc) return rc;
     if (nbatch < 0) return FMPC_ERR_DIM;
@@ -457,7 +472,7 @@ int fmpc_step_d(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *
     if ((X0 == nullptr) != (U0 == nullptr)) return FMPC_ERR_INIT_SIZE;
     if (nbatch == 0) return FMPC_OK;
     CU_OK(cudaSetDevice(h->device));
-    return step_device(h, p, nbatch, x0, x0_pre, w, xf, X0, U0, nu0, X, U, status, iters,
+    return step_device(h, p, nbatch, x0, x0_pre, u_prev, w, xf, X0, U0, nu0, X, U, status, iters,
                        stream ? (cudaStream_t)stream : h->stream);
 }
 
@@ -465,8 +480,8 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
               const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0,
               const double *nu0, double *X, double *U, int *status, int *iters, double *telapsed)
 {
-    (void)u_prev;
     if (!h || !x0 || !X || !U) return FMPC_ERR_NULL;
+    if (h->ramp && !u_prev) return FMPC_ERR_U_BOUND_SIZE;
     int rc = validate_params(p);
     if (rc) return rc;
     if (nbatch < 0) return FMPC_ERR_DIM;
@@ -480,7 +495,7 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     const size_t nb = (size_t)nbatch, NBn = (size_t)(T + (xf ? 1 : 0)) * n;
     cudaStream_t st = h->stream;
     if (h->d_x0.ensure(nb * n * 8) || h->d_x0pre.ensure(nb * n * 8) || h->d_w.ensure(nb * T * n * 8) || h->d_xf.ensure(nb * n * 8) ||
-        h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
+        h->d_uprev.ensure(nb * m * 8) || h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
         h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4))
         return FMPC_ERR_CUDA;
     const double *nu_src = nu0;
@@ -506,6 +521,7 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
             const size_t b0 = (size_t)ci * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
             CU_OK(cudaMemcpyAsync(h->d_x0.as<double>() + b0 * n, x0 + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
             if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.as<double>() + b0 * n, x0_pre + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
+            if (u_prev && h->ramp) CU_OK(cudaMemcpyAsync(h->d_uprev.as<double>() + b0 * m, u_prev + b0 * m, cb * m * 8, cudaMemcpyHostToDevice, si));
             if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, w + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
             if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.as<double>() + b0 * n, xf + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
             if (X0) {
@@ -517,7 +533,7 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
             CU_OK(cudaStreamWaitEvent(st, h->ev_in[ci], 0));
             if (ci == 0) CU_OK(cudaEventRecord(h->ev0, st));
             rc = step_device(h, p, (int)cb, h->d_x0.as<double>() + b0 * n, x0_pre ? h->d_x0pre.as<double>() + b0 * n : nullptr,
-                             w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
+                             (u_prev && h->ramp) ? h->d_uprev.as<double>() + b0 * m : nullptr, w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
                              X0 ? h->d_X.as<double>() + b0 * Tn : nullptr, X0 ? h->d_U.as<double>() + b0 * Tm : nullptr,
                              h->d_nu0.as<double>() + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
                              h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, st, ci > 0);
@@ -700,7 +716,7 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, co
                                k == 0, st);
         CU_OK(cudaGetLastError());
         h->launches += 1;
-        rc = step_device(h, p, nbatch, h->d_x0.as<double>(), h->d_x0pre.as<double>(), nullptr, nullptr,
+        rc = step_device(h, p, nbatch, h->d_x0.as<double>(), h->d_x0pre.as<double>(), h->d_uprev.as<double>(), nullptr, nullptr,
                          k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(), h->d_nu0.as<double>(),
                          h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
         if (rc) return rc;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 // Problem-constant device data of one handle.  All n x n "blocks" are ROW-major on the device
 // (the host layer transposes MATLAB's column-major input once, at fmpc_create).
@@ -37,7 +38,7 @@ struct StepArgs {
     double kappa;
     int niters, ls_max;
     double alpha, beta, tol_r, tol_p;
-    const double *x0, *x0_pre, *w, *xf, *X0, *U0, *nu0;
+    const double *x0, *x0_pre, *u_prev, *w, *xf, *X0, *U0, *nu0;
     double *X, *U;
     int *status, *iters;
     unsigned int *counter;              // dynamic instance counter (zeroed before launch)
@@ -71,10 +72,25 @@ struct WsLayout {
     }
 };
 
+// Device tables of the general-structure kernel (fmpc_kernel_gen.cu): C as the reference builds it (one dense row
+// window per block row), the u-column blocks of every block row, the iterate-independent x part of the Schur
+// complement, dense 2Q / inv(2Q), ramp-rate bounds.
+struct GenSys {
+    int n, m, T, N, ramp, ldyx, panel_rows;
+    const double *cw;                       // pool of window matrices, row-major n x cw_len[i]
+    const int *cw_ptr, *cw_off, *cw_len;    // per block row (T+1): offset into cw, first column, width
+    const double *cu, *cut;                 // pool of n x m blocks C[i, u_t] (row-major) and their transposes (m x n)
+    const int *ue_cnt, *ue_t, *ue_ptr;      // per block row: number of u blocks (<= 4), their stages, offsets into cu
+    const double *Yx;                       // ((T+1) n)^2 row-major: C_x inv(Phi_xx) C_x'
+    const double *Q2, *Q2f, *Qi, *Qif;      // n x n row-major: 2Q, 2Qf and their inverses
+    const double *dumin, *dumax;            // m
+};
+
 // status words (mirror include/fmpc.h)
 enum { ST_OK = 0, ST_EARLY_EXIT = 1, ST_NOT_PD = 2, ST_LS_MAX = 3, ST_NONFINITE = 4 };
 
-// use_mma: 0 = generic CTA kernel (any n), 1 = CTA-per-instance DMMA kernel (n <= 32), 2 = warp-per-instance DMMA kernel (n <= 32)
+// use_mma: 0 = generic CTA kernel (any n), 1 = CTA-per-instance DMMA kernel (n <= 32), 2 = warp-per-instance DMMA kernel (n <= 32),
+//          3 = general-structure kernel (ramp rows / literal VAR_1 columns / dense Q)
 struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; int slots; size_t ws_stride; };
 
 // kernels.cu
@@ -92,3 +108,8 @@ void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunch
 // kernel_warp.cu : warp-per-instance DMMA path (n <= 32), the default
 int  fmpc_warp_config(const DevSys &S, int device, SolveLaunchCfg *cfg);         // 0 ok, <0 not applicable
 void fmpc_launch_solve_warp(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
+
+// kernel_gen.cu : general-structure path (VAR_1 ramp rows, literal VAR_1 column placement, dense Q / Qf)
+struct fmpc_sys;
+int  fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void *> &allocs, SolveLaunchCfg *cfg);   // FMPC_* code
+void fmpc_launch_solve_gen(const DevSys &S, const GenSys &G, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);

@@ -66,7 +66,7 @@ class FastMPCBatch:
     """One fmpc_handle: shared problem data + workspaces for up to `max_batch` instances."""
 
     def __init__(self, A1, A2, B, Q, R, Qf, u_min, u_max, T, x_min=None, x_max=None, q=None, r=None, qf=None,
-                 du_min=None, du_max=None, ramp_rows=False, max_batch=1, device=0):
+                 du_min=None, du_max=None, ramp_rows=False, max_batch=1, device=0, var1_literal_bug=False):
         L = load_library()
         self._L = L
         self.var_order = 1 if _isempty(A2) else 2
@@ -91,6 +91,8 @@ class FastMPCBatch:
         s.x_min, s.x_max, s.u_min, s.u_max = P(self._xmin), P(self._xmax), P(self._umin), P(self._umax)
         s.du_min, s.du_max = P(self._dumin), P(self._dumax)
         s.ramp_rows = 1 if ramp_rows else 0
+        s.var1_literal_bug = 1 if (var1_literal_bug and self.var_order == 1) else 0
+        self.ramp_rows = bool(ramp_rows)
         self.max_batch = int(max_batch)
         self.device = int(device)
         h = C.c_void_p()
@@ -315,16 +317,18 @@ class Fast_MPC2:
         return n, m
 
     _ramp_rows = False
+    _literal_bug = False
 
     def _handle(self) -> FastMPCBatch:
         keys = [self.A1, self.A2, self.B, self.Q, self.R, self.Qf, self.q, self.r, self.qf, self.x_min, self.x_max,
-                self.u_min, self.u_max, np.array([self.T, self.var_order, self.device, int(self._ramp_rows)], dtype=np.float64)]
+                self.u_min, self.u_max, np.array([self.T, self.var_order, self.device, int(self._ramp_rows),
+                                                  int(self._literal_bug)], dtype=np.float64)]
         if self._ramp_rows:
             keys += [self.du_min, self.du_max]
         return _cached_handle(keys, lambda: FastMPCBatch(
             self.A1, self.A2 if self.var_order == 2 else None, self.B, self.Q, self.R, self.Qf, self.u_min, self.u_max,
             self.T, self.x_min, self.x_max, self.q, self.r, self.qf, self.du_min, self.du_max, self._ramp_rows,
-            max_batch=1, device=self.device))
+            max_batch=1, device=self.device, var1_literal_bug=self._literal_bug))
 
     def _run(self, nw, k, nu0, frontend=None, k_min=None, k_max=None):
         n, m = self._validate()
@@ -383,14 +387,26 @@ class Fast_MPC2:
 class Fast_MPC2_VAR1(Fast_MPC2):
     """VAR_1/Fast_MPC2.m -- 21 constructor arguments (no x0_pre, single A).
 
-    The equality rows follow the CORRECTED structure of VAR_1/fast_mpc_eq_const.m (its second block
-    row is written at column n instead of m+1; the literal bug is reproduced only by the
-    oracle).  `ramp_rows=True` asks for VAR_1's ramp-rate rows (fast_mpc_ineq_const.m:58-79)."""
+    The defaults reproduce the reference's VAR_1 exactly as written: ramp-rate rows enabled
+    (VAR_1/fast_mpc_ineq_const.m:58-79) and the second block row of C written at columns n : 3n+m-1
+    (VAR_1/fast_mpc_eq_const.m:34-37).  `literal_bug=False` selects the corrected
+    placement m+1 : 2(n+m) (= VAR_2's code with A2 = 0); `ramp_rows=False` drops the ramp rows (then,
+    with diagonal Q/R and the corrected C, the solve runs on the block-banded DMMA kernels)."""
 
     var_order = 1
 
     def __init__(self, Q, R, S, Qf, q, r, qf, xmin, xmax, umin, umax, dumin, dumax, T, x0, u_prev, A, B, w, xf,
-                 x_init, ramp_rows=False):
+                 x_init, ramp_rows=True, literal_bug=True):
         super().__init__(Q, R, S, Qf, q, r, qf, xmin, xmax, umin, umax, dumin, dumax, T, x0, None, u_prev, A, None,
                          B, w, xf, x_init)
         self._ramp_rows = bool(ramp_rows)
+        self._literal_bug = bool(literal_bug)
+
+    def _validate(self):
+        n, m = super()._validate()
+        if self._ramp_rows:
+            if self.du_min is None or self.du_max is None or self.du_min.shape[0] != m or self.du_max.shape[0] != m:
+                raise ValueError("Check cotrol iequality constraint dimension")
+            if self.u_prev is None or self.u_prev.shape[0] != m:
+                raise ValueError("Arrays have incompatible sizes for this operation (u_prev + du_max)")
+        return n, m

@@ -12,6 +12,8 @@ classdef Fast_MPC2_b200
         x_final; x_init
         nu0 = []       % optional explicit dual start (inf_newton_solver.m:2 draws rand(); [] = MATLAB default stream)
         device = 0
+        ramp_rows = 0          % 1: VAR_1 ramp-rate rows (VAR_1/fast_mpc_ineq_const.m:58-79); needs u_prev, du_min, du_max
+        var1_literal_bug = 0   % 1 (VAR_1 only): second block row of C at columns n:3n+m-1 as VAR_1/fast_mpc_eq_const.m:34-37
     end
     methods
         function cs = Fast_MPC2_b200(Q,R,S,Qf,q,r,qf,xmin,xmax,umin,umax,dumin,dumax,T,x0,x0_pre,u_prev,A1,A2,B,w,xf,x_init)
@@ -61,13 +63,14 @@ classdef Fast_MPC2_b200
             persistent cache
             if isempty(cache), cache = containers.Map('KeyType', 'char', 'ValueType', 'any'); end
             [n, m] = size(obj.B);
-            sys = struct('n', n, 'm', m, 'T', obj.T, 'var_order', 1 + ~isempty(obj.A2), 'ramp_rows', 0, ...
+            sys = struct('n', n, 'm', m, 'T', obj.T, 'var_order', 1 + ~isempty(obj.A2), 'ramp_rows', obj.ramp_rows, ...
+                         'var1_literal_bug', obj.var1_literal_bug, ...
                          'A1', obj.A1, 'A2', obj.A2, 'B', obj.B, 'Q', obj.Q, 'R', obj.R, 'Qf', obj.Qf, 'q', obj.q, 'r', obj.r, ...
                          'qf', obj.qf, 'x_min', obj.x_min, 'x_max', obj.x_max, 'u_min', obj.u_min, 'u_max', obj.u_max, ...
                          'du_min', obj.du_min, 'du_max', obj.du_max);
-            key = sprintf('%d_%d_%d_%d_%.17g', n, m, obj.T, max(nb, 1), ...
+            key = sprintf('%d_%d_%d_%d_%d_%d_%.17g', n, m, obj.T, max(nb, 1), obj.ramp_rows, obj.var1_literal_bug, ...
                           sum(obj.A1(:)) + 3*sum(obj.B(:)) + 5*sum(obj.Q(:)) + 7*sum(obj.R(:)) + 11*sum(obj.Qf(:)) + ...
-                          13*sum(obj.u_min) + 17*sum(obj.u_max) + 19*sum(obj.A2(:)));
+                          13*sum(obj.u_min) + 17*sum(obj.u_max) + 19*sum(obj.A2(:)) + 23*obj.ramp_rows*(sum(obj.du_min) + 2*sum(obj.du_max)));
             if ~isKey(cache, key), cache(key) = fmpc_mex('create', sys, max(nb, 1), obj.device); end
             h = cache(key);
         end

@@ -105,6 +105,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         memset(&sys, 0, sizeof sys);
         sys.n = fieldi(s, "n", 0); sys.m = fieldi(s, "m", 0); sys.T = fieldi(s, "T", 0);
         sys.var_order = fieldi(s, "var_order", 2); sys.ramp_rows = fieldi(s, "ramp_rows", 0);
+        sys.var1_literal_bug = fieldi(s, "var1_literal_bug", 0);
         sys.A1 = fieldp(s, "A1"); sys.A2 = fieldp(s, "A2"); sys.B = fieldp(s, "B");
         sys.Q = fieldp(s, "Q"); sys.R = fieldp(s, "R"); sys.Qf = fieldp(s, "Qf");
         sys.q = fieldp(s, "q"); sys.r = fieldp(s, "r"); sys.qf = fieldp(s, "qf");

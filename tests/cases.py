@@ -65,3 +65,43 @@ def ref_solve(fref, c, niters, kappa, **kw):
 def relerr(a, b):
     """Normwise (max-norm) relative error per array, SURVEY.md 8c."""
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def var1_literal_case(seed, n, m, T, nb, umax, du, xf=False, dense_q=False):
+    """VAR(1) problem with ramp-rate bounds +-du, a warm start that respects them, and u_prev."""
+    c = small_problem(seed, n, m, T, nb, umax, a2=False, xf=xf, warm=True)
+    rs = np.random.RandomState(seed + 1000)
+    u_prev = 0.3 * umax * rs.randn(nb, m).clip(-2, 2)
+    U0 = u_prev[:, None, :] + np.cumsum(0.3 * du * rs.randn(nb, T, m).clip(-2, 2), axis=1)
+    c["U0"] = np.clip(U0, -0.95 * umax, 0.95 * umax)
+    c["u_prev"] = u_prev
+    c["du_min"], c["du_max"] = -du * np.ones(m), du * np.ones(m)
+    if dense_q:
+        G = rs.randn(n, n)
+        c["Q"] = G @ G.T / n + np.eye(n)
+        G = rs.randn(n, n)
+        c["Qf"] = 2 * (G @ G.T / n + np.eye(n))
+    return c
+
+
+def var1_literal_dense(fd, c, b, niters, kappa, ramp=True, bug=True):
+    """One instance through the literal dense oracle's VAR_1 class (ramp rows / literal C placement on request)."""
+    g = lambda k: None if c.get(k) is None else c[k][b]
+    z0 = None if c["X0"] is None else z0_of(c)[b]
+    du_min = c.get("du_min", -np.ones(c["m"]))
+    du_max = c.get("du_max", np.ones(c["m"]))
+    u_prev = g("u_prev") if c.get("u_prev") is not None else np.zeros(c["m"])
+    if c["A2"] is None:
+        obj = fd.Fast_MPC2_VAR1(c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"],
+                                c["u_max"], du_min, du_max, c["T"], c["x0"][b], u_prev, c["A1"], c["B"], g("w"), g("xf"), z0,
+                                literal_bug=bug)
+        if not ramp:
+            obj.inequality_const = lambda: fd.fast_mpc_ineq_const_var2(obj)
+    else:
+        obj = fd.Fast_MPC2(c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"],
+                           c["u_max"], du_min, du_max, c["T"], c["x0"][b], g("x0_pre"), u_prev, c["A1"], c["A2"], c["B"],
+                           g("w"), g("xf"), z0)
+        if ramp:
+            obj.inequality_const = lambda: fd.fast_mpc_ineq_const_var1(obj)
+    z = obj.mpc_fixed_log_newton(niters, kappa, nu0=c["nu0"][b])
+    return z, obj.last_stats

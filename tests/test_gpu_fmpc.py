@@ -177,7 +177,7 @@ def test_var1_class_mirror(pk):
     c = small_problem(25, 6, 4, 5, 1, 0.4, a2=False)
     args = (c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"], c["u_max"],
             -np.ones(4), np.ones(4), c["T"], c["x0"][0], np.zeros(4), c["A1"], c["B"], c["w"][0], None, None)
-    z = pk.Fast_MPC2_VAR1(*args).mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])
+    z = pk.Fast_MPC2_VAR1(*args, ramp_rows=False, literal_bug=False).mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])
     o = fd.Fast_MPC2_VAR1(*args, literal_bug=False)
     o.inequality_const = lambda: fd.fast_mpc_ineq_const_var2(o)
     assert relerr(z, o.mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])) < TOL

@@ -1,0 +1,165 @@
+"""GPU parity tests of the general-structure kernel (VAR_1 ramp-rate rows, the literal VAR_1 placement of the
+second block row of C, dense Q / Qf) through the C-ABI, against the literal dense oracle (live, at sizes it
+finishes in seconds) and the committed var1lit_* golden fixtures.  Tolerance 1e-9 relative per array on U and X."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from cases import relerr, small_problem, var1_literal_case, var1_literal_dense, z0_of
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+VAR1_FIXTURES = sorted(glob.glob(os.path.join(GOLD, "var1lit_*.npz")))
+
+
+def gen_handle(pk, c, ramp, bug, max_batch=None):
+    return pk.FastMPCBatch(c["A1"], c["A2"], c["B"], c["Q"], c["R"], c["Qf"], c["u_min"], c["u_max"], c["T"],
+                           c["x_min"], c["x_max"], du_min=c.get("du_min"), du_max=c.get("du_max"), ramp_rows=ramp,
+                           var1_literal_bug=bug, max_batch=max_batch or c["nb"])
+
+
+def gen_solve(pk, c, niters, kappa, ramp, bug, **kw):
+    hb = gen_handle(pk, c, ramp, bug)
+    assert hb.kernel_kind == 3
+    out = hb.step(c["x0"], c["x0_pre"], c["w"], c["xf"], c["X0"], c["U0"], c["nu0"], u_prev=c.get("u_prev"), kappa=kappa,
+                  niters=niters, **kw)
+    hb.close()
+    return out
+
+
+def check_against_dense(pk, c, niters, kappa, ramp, bug):
+    from oracle import fastmpc_dense as fd
+    out = gen_solve(pk, c, niters, kappa, ramp, bug)
+    for b in range(c["nb"]):
+        z, st = var1_literal_dense(fd, c, b, niters, kappa, ramp=ramp, bug=bug)
+        U, X = fd.deinterleave(z, c["n"], c["m"], c["T"])
+        assert relerr(out["U"][b], U.T) < TOL, f"U instance {b}"
+        assert relerr(out["X"][b], X.T) < TOL, f"X instance {b}"
+        assert out["iters"][b] == st["iters"]
+        assert (out["status"][b] == 1) == bool(st["early_exit"])
+
+
+GEN_CASES = [
+    # seed n  m  T  nb umax  du   xf     ramp  bug   denseQ
+    (301, 6, 9, 6, 3, 0.6, 0.15, False, True, True, False),     # the reference's VAR_1 as written
+    (302, 6, 9, 6, 3, 0.6, 0.15, False, True, False, False),    # ramp rows, corrected C
+    (303, 6, 9, 6, 3, 0.6, 0.15, False, False, True, False),    # literal C, box rows only
+    (304, 7, 5, 8, 3, 0.5, 0.10, True, True, False, False),     # ramp rows + terminal row x_T = xf
+    (305, 5, 12, 4, 2, 0.5, 0.10, True, True, True, False),     # literal C + xf (n < m + 1)
+    (306, 9, 4, 5, 2, 0.5, 0.10, False, True, True, False),     # n > m + 1: the mis-placed row reaches into x_2
+    (307, 6, 9, 6, 3, 0.6, 0.15, False, False, False, True),    # dense Q / Qf only
+    (308, 8, 7, 7, 2, 0.6, 0.15, True, True, True, True),       # everything at once
+    (309, 33, 20, 6, 2, 0.5, 0.10, False, True, True, False),   # n > 32
+    (310, 3, 2, 3, 2, 0.5, 0.10, False, True, True, False),     # smallest horizon the literal C supports
+]
+
+
+@pytest.mark.parametrize("cfg", GEN_CASES, ids=lambda g: f"s{g[0]}_n{g[1]}m{g[2]}T{g[3]}")
+def test_gen_kernel_matches_dense_oracle(pk, cfg):
+    seed, n, m, T, nb, umax, du, xf, ramp, bug, dq = cfg
+    c = var1_literal_case(seed, n, m, T, nb, umax, du, xf=xf, dense_q=dq)
+    check_against_dense(pk, c, 5, 0.01, ramp, bug)
+
+
+def test_gen_kernel_feasible_regime_converges(pk):
+    """Small states: iterates stay inside box and ramp bounds, the early-exit test fires like the oracle's."""
+    c = var1_literal_case(203, 6, 9, 6, 3, 0.6, 0.15)
+    c["x0"] *= 0.2; c["w"] *= 0.2; c["X0"] *= 0.2
+    c["U0"] = 0.2 * c["U0"]; c["u_prev"] = 0.2 * c["u_prev"]
+    check_against_dense(pk, c, 8, 0.01, True, True)
+    out = gen_solve(pk, c, 8, 0.01, True, True)
+    d = np.diff(np.concatenate([c["u_prev"][:, None, :], out["U"]], axis=1), axis=1)
+    assert np.abs(d).max() < 0.15 and np.abs(out["U"]).max() < 0.6
+    assert (out["status"] == 1).all()
+
+
+def test_gen_var2_with_ramp_rows_and_cold_start(pk):
+    """ramp_rows on the two-lag model (the rows VAR_2/fast_mpc_ineq_const.m:58-82 has commented out), cold start."""
+    from oracle import fastmpc_dense as fd
+    c = small_problem(311, 6, 5, 6, 2, 0.8)
+    c["du_min"], c["du_max"] = -0.5 * np.ones(5), 0.5 * np.ones(5)
+    c["u_prev"] = 0.1 * np.random.RandomState(5).randn(2, 5)
+    out = gen_solve(pk, c, 4, 0.01, True, False)
+    for b in range(2):
+        z, st = var1_literal_dense(fd, c, b, 4, 0.01, ramp=True, bug=False)
+        U, X = fd.deinterleave(z, 6, 5, 6)
+        assert relerr(out["U"][b], U.T) < TOL and relerr(out["X"][b], X.T) < TOL
+
+
+@pytest.mark.parametrize("path", VAR1_FIXTURES, ids=lambda p: os.path.basename(p)[8:-4])
+def test_gen_kernel_matches_golden(pk, path):
+    g = np.load(path)
+    c = {k: g[k] for k in g.files}
+    for k in ("n", "m", "T", "nb", "niters"):
+        c[k] = int(c[k])
+    for k in ("A2", "x0_pre", "xf"):
+        c.setdefault(k, None)
+    out = gen_solve(pk, c, c["niters"], float(c["kappa"]), bool(c["ramp"]), bool(c["bug"]))
+    for b in range(c["nb"]):
+        assert relerr(out["U"][b], c["U"][b]) < TOL and relerr(out["X"][b], c["X"][b]) < TOL
+    assert np.array_equal(out["iters"], c["iters"])
+
+
+def test_var1_class_is_the_reference_by_default(pk):
+    """Fast_MPC2_VAR1 with the reference's 21 ctor arguments = ramp rows + literal C (VAR_1/Fast_MPC2.m:26-51)."""
+    from oracle import fastmpc_dense as fd
+    c = var1_literal_case(312, 6, 9, 6, 1, 0.6, 0.15)
+    args = (c["Q"], c["R"], None, c["Qf"], None, None, None, c["x_min"], c["x_max"], c["u_min"], c["u_max"],
+            c["du_min"], c["du_max"], c["T"], c["x0"][0], c["u_prev"][0], c["A1"], c["B"], c["w"][0], None, z0_of(c)[0])
+    z = pk.Fast_MPC2_VAR1(*args).mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])
+    zr = fd.Fast_MPC2_VAR1(*args).mpc_fixed_log_newton(5, 0.01, nu0=c["nu0"][0])
+    assert relerr(z, zr) < TOL
+    # kappa-continuation front-end on the same path
+    nouter = len(fd.Fast_MPC2.kappa_schedule(c["T"] * (c["n"] + c["m"])))
+    nus = np.random.RandomState(1).rand(nouter, c["T"] * c["n"])
+    z2 = pk.Fast_MPC2_VAR1(*args).mpc_fixed_newton(2, nu0=nus)
+    zr2 = fd.Fast_MPC2_VAR1(*args).mpc_fixed_newton(2, nu0_list=list(nus))
+    assert relerr(z2, zr2) < TOL
+
+
+def test_gen_closed_loop_ramp(pk):
+    """fmpc_closed_loop on the ramp-row path: u_prev of step k is U(:,0) of step k-1 (kept on the device)."""
+    from mpc_sensorlessao_b200 import synth
+    from oracle import fastmpc_dense as fd
+    p = synth.make_problem(2, 4, var_order=1, m1=3, u_bound=5.0)
+    nb, K = 2, 3
+    a = synth.aberrations(p, nb, K, seed=3, amp=0.2)
+    du = 0.5
+    hb = pk.FastMPCBatch(p.A1, None, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max,
+                         du_min=-du * np.ones(p.m), du_max=du * np.ones(p.m), ramp_rows=True, var1_literal_bug=True, max_batch=nb)
+    nu0 = np.random.RandomState(9).rand(K, nb, p.T * p.n)
+    out = hb.closed_loop(a, nu0=nu0, kappa=0.01, niters=3)
+    hb.close()
+    for b in range(nb):
+        u_prev = np.zeros(p.m); x0 = np.zeros(p.n); z = None
+        for k in range(K):
+            x0 = a[b, k] + p.B @ u_prev
+            if z is not None:     # shift the warm start one stage, last stage repeated
+                Z = z.reshape(p.T, p.n + p.m)
+                z = np.vstack([Z[1:], Z[-1:]]).reshape(-1)
+            o = fd.Fast_MPC2_VAR1(p.Q, p.R, None, p.Qf, None, None, None, p.x_min, p.x_max, p.u_min, p.u_max,
+                                  -du * np.ones(p.m), du * np.ones(p.m), p.T, x0, u_prev, p.A1, p.B, np.zeros(p.T * p.n), None, z)
+            z = o.mpc_fixed_log_newton(3, 0.01, nu0=nu0[k, b])
+            u_prev = z[:p.m].copy()
+            assert relerr(out["U_acc"][b, k], u_prev) < TOL, (b, k)
+            assert relerr(out["X_acc"][b, k], x0) < 1e-12
+
+
+def test_gen_argument_errors(pk):
+    c = var1_literal_case(313, 6, 9, 6, 2, 0.6, 0.15)
+    hb = gen_handle(pk, c, True, True)
+    with pytest.raises(pk.FmpcError) as e:       # ramp rows need u_prev
+        hb.step(c["x0"], None, c["w"], None, c["X0"], c["U0"], c["nu0"], u_prev=None)
+    assert e.value.code == -7
+    hb.close()
+    Rd = c["R"].copy(); Rd[0, 1] = Rd[1, 0] = 0.1
+    with pytest.raises(pk.FmpcError) as e:       # non-diagonal R is the one input no kernel covers
+        pk.FastMPCBatch(c["A1"], None, c["B"], c["Q"], Rd, c["Qf"], c["u_min"], c["u_max"], c["T"], c["x_min"], c["x_max"])
+    assert e.value.code == -14
+    c2 = var1_literal_case(314, 6, 9, 2, 1, 0.6, 0.15)
+    with pytest.raises(pk.FmpcError) as e:       # literal C with T < 3: fast_mpc_eq_const.m:55 rewrites the row itself
+        gen_handle(pk, c2, False, True)
+    assert e.value.code == -14
