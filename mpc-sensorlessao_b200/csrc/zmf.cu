@@ -6,8 +6,22 @@
 // W = inv(Z'Z) Z' (cond(Z) = 3.8 at N = 6, 5.0 at N = 10: normal equations are safe at 1e-10),
 // scatters it to the full frame (zeros outside the pupil) and the device computes
 // coef = W * frames, an HBM-streaming fp64 GEMM with M = nmodes, K = nL^2, N = nframes.
+//
+// The GEMM is balanced between the two rooflines (2 nmodes npix_in flop per 8 nL^2 bytes = 5.4 flop/B at N = 6, the
+// FP64 ridge of a B200 is ~5.7), so the product kernel (zmf_fit_dmma_kernel) runs it on the FP64 tensor pipe:
+//   * K is cut into 8-pixel groups; groups wholly outside the pupil are dropped (their bytes are never read),
+//     partially covered ones carry a pixel mask so that NaNs outside the pupil (zernmodfit.m:30) never reach a DMMA;
+//   * the frames (A operand, M = 8 frames per tile) go HBM -> registers directly: every element is needed by exactly one
+//     lane, each lane loads 16 B (2 k-steps), 4 lanes cover one 64-byte run of a frame, a 4-group register ring keeps
+//     ~4 KB per warp in flight;
+//   * W (B operand) is pre-permuted on the host into DMMA fragment order, so a chunk of groups is ONE contiguous block:
+//     it is brought into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, 3 stages) and read back with
+//     conflict-free 128-bit loads; MT frame tiles per warp share every B fragment;
+//   * split-K over blockIdx.y (deterministic: partial sums to a scratch buffer, then a small reduction kernel) fills
+//     the 148 SMs when there are few frames and removes the wave-quantisation tail when there are many.
 #include <cuda_runtime.h>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -43,6 +57,13 @@ struct zmf_handle {
     unsigned char *d_mask = nullptr;
     double *d_frames = nullptr, *d_coef = nullptr;
     size_t cap_frames = 0;
+    // DMMA path
+    double *d_Wf = nullptr;                // [group][ntile][lane][2] fragment-ordered W
+    unsigned *d_ginfo = nullptr;           // per group: (first pixel / 8) | (pixel mask << 24)
+    int ngroups = 0, ntiles = 0;
+    double *d_part = nullptr;              // split-K partial sums [ksplit][nframes][8 ntiles]
+    size_t part_doubles = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     long long launches = 0;
@@ -99,6 +120,178 @@ __global__ void __launch_bounds__(NT) zmf_fit_kernel(const double *__restrict__ 
         __syncthreads();
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// DMMA kernel (see the header comment).  Grid = (frame blocks of NW * 8 MT frames, ksplit).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int ZSTAGES = 3;
+template <int NT> struct ZChunk { static constexpr int CH = (NT <= 4) ? 16 : 8; };     // groups per shared-memory stage
+constexpr int ZRING = 4;                                                             // frame-load ring depth (groups)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zdmma(double (&c)[2], const double a, const double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int NT, int MT, int NW>
+__global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__restrict__ Wf, const unsigned *__restrict__ ginfo, int ngroups,
+                                                               int groups_per_split, const double *__restrict__ frames,
+                                                               double *__restrict__ out, int out_ld, size_t out_split_stride,
+                                                               int npix, int nmodes, int nframes)
+{
+    constexpr int CH = ZChunk<NT>::CH, GD = NT * 64;            // doubles of W per group
+    extern __shared__ __align__(128) double wbuf[];             // ZSTAGES x CH x GD
+    __shared__ __align__(8) unsigned long long bars[ZSTAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+    const int g_begin = blockIdx.y * groups_per_split;
+    const int g_end = min(ngroups, g_begin + groups_per_split);
+    const int nch = (g_end - g_begin + CH - 1) / CH;
+    const int f0 = (blockIdx.x * NW + warp) * 8 * MT;
+
+    if (tid == 0) {
+        for (int s = 0; s < ZSTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int c) {       // thread 0: chunk c of this split -> stage c % ZSTAGES
+        const int s = c % ZSTAGES, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
+        const unsigned bytes = (unsigned)ng * GD * 8u, bar = smem_u32(&bars[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(wbuf + (size_t)s * CH * GD)), "l"(Wf + (size_t)g0 * GD), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0) for (int c = 0; c < ZSTAGES && c < nch; ++c) issue(c);
+
+    // frame rows of this lane (rows past the last frame alias the last one: loaded, never stored)
+    const double *fr[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) fr[mt] = frames + (size_t)min(f0 + 8 * mt + gq, nframes - 1) * npix + 2 * q;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    double2 ring[ZRING][MT];
+    unsigned rinfo[ZRING];
+    auto load = [&](int d, int g) {
+        const unsigned info = __ldg(ginfo + min(g, ngroups - 1));
+        rinfo[d] = info;
+        const size_t off = (size_t)(info & 0xFFFFFFu) * 8;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) ring[d][mt] = __ldcs(reinterpret_cast<const double2 *>(fr[mt] + off));
+    };
+#pragma unroll
+    for (int d = 0; d < ZRING; ++d) load(d, g_begin + d);
+
+    for (int c = 0; c < nch; ++c) {
+        const int s = c % ZSTAGES;
+        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ZSTAGES) & 1);
+        while (!mbar_try_wait(bar, parity)) { }
+        const double *wb = wbuf + (size_t)s * CH * GD + 2 * lane;
+        const int g0 = g_begin + c * CH;
+#pragma unroll 1
+        for (int gi = 0; gi < CH; gi += ZRING) {
+#pragma unroll
+            for (int d = 0; d < ZRING; ++d) {
+                const int g = g0 + gi + d;
+                if (g < g_end) {
+                    double2 av[MT];
+                    const unsigned mk = rinfo[d] >> 24;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) av[mt] = ring[d][mt];
+                    if (mk != 0xFFu) {                   // pupil edge: pixels outside may hold NaN -> exact zeros
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            if (!((mk >> (2 * q)) & 1u)) av[mt].x = 0.0;
+                            if (!((mk >> (2 * q + 1)) & 1u)) av[mt].y = 0.0;
+                        }
+                    }
+                    load(d, g + ZRING);
+                    const double *wg = wb + (size_t)(gi + d) * GD;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double2 b = *reinterpret_cast<const double2 *>(wg + nt * 64);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) { zdmma(acc[mt][nt], av[mt].x, b.x); zdmma(acc[mt][nt], av[mt].y, b.y); }
+                    }
+                }
+            }
+        }
+        __syncthreads();                                 // every warp is done with stage s
+        if (tid == 0 && c + ZSTAGES < nch) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + ZSTAGES);
+        }
+    }
+    double *o = out + (size_t)blockIdx.y * out_split_stride;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int f = f0 + 8 * mt + gq;
+        if (f < nframes) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = 8 * nt + 2 * q + e;
+                    if (j < out_ld && (out_ld != nmodes || j < nmodes)) o[(size_t)f * out_ld + j] = acc[mt][nt][e];
+                }
+        }
+    }
+}
+
+// coef[f][j] = sum over splits of part[split][f][j]   (fixed order: deterministic)
+__global__ void zmf_reduce_kernel(const double *__restrict__ part, int ksplit, size_t split_stride, int ld, double *__restrict__ coef,
+                                  int nmodes, int nframes)
+{
+    const size_t tot = (size_t)nframes * nmodes;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = e / nmodes;
+        const int j = (int)(e - f * nmodes);
+        double s = 0.0;
+        for (int k = 0; k < ksplit; ++k) s += part[(size_t)k * split_stride + f * ld + j];
+        coef[e] = s;
+    }
+}
+
+template <int NT, int MT, int NW>
+cudaError_t zmf_launch_dmma(const zmf_handle *h, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
+                            int ksplit, int gps, cudaStream_t st)
+{
+    constexpr int CH = ZChunk<NT>::CH;
+    const size_t smem = (size_t)ZSTAGES * CH * NT * 64 * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((nframes + NW * 8 * MT - 1) / (NW * 8 * MT), ksplit);
+    zmf_fit_dmma_kernel<NT, MT, NW><<<grid, NW * 32, smem, st>>>(h->d_Wf, h->d_ginfo, h->ngroups, gps, frames, out, out_ld, split_stride,
+                                                                 h->npix, h->nmodes, nframes);
+    return cudaGetLastError();
+}
+
+template <int NT>
+cudaError_t zmf_launch_nt(const zmf_handle *h, int mt, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
+                          int ksplit, int gps, cudaStream_t st)
+{
+    if (mt == 2) return zmf_launch_dmma<NT, 2, 8>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    return zmf_launch_dmma<NT, 1, 8>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+}
+
+} // namespace
 
 extern "C" {
 
@@ -171,6 +364,34 @@ int zmf_create(zmf_handle **out, int nL, int N, int max_frames, int device)
     bool ok = cudaMalloc(&h->d_W, W.size() * 8) == cudaSuccess && cudaMalloc(&h->d_mask, h->npix) == cudaSuccess;
     ok = ok && cudaMemcpy(h->d_W, W.data(), W.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(h->d_mask, h->mask.data(), h->npix, cudaMemcpyHostToDevice) == cudaSuccess;
+    {   // DMMA path tables: needs 16-byte aligned frame rows and whole 8-pixel groups (nL % 4 == 0) and <= 72 modes
+        h->sm_count = prop.multiProcessorCount;
+        h->ntiles = (M + 7) / 8;
+        if (h->npix % 8 == 0 && h->ntiles <= 9) {
+            std::vector<unsigned> ginfo;
+            for (int g = 0; g < h->npix / 8; ++g) {
+                unsigned mk = 0;
+                for (int e = 0; e < 8; ++e) if (h->mask[(size_t)8 * g + e]) mk |= 1u << e;
+                if (mk) ginfo.push_back((unsigned)g | (mk << 24));
+            }
+            h->ngroups = (int)ginfo.size();
+            const int NTl = h->ntiles;
+            std::vector<double> Wf((size_t)h->ngroups * NTl * 64, 0.0);
+            for (int gi = 0; gi < h->ngroups; ++gi) {
+                const size_t p0 = (size_t)(ginfo[gi] & 0xFFFFFFu) * 8;
+                for (int nt = 0; nt < NTl; ++nt)
+                    for (int ln = 0; ln < 32; ++ln)
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 8 * nt + (ln >> 2);
+                            const size_t px = p0 + 2 * (ln & 3) + e;
+                            Wf[(((size_t)gi * NTl + nt) * 32 + ln) * 2 + e] = (j < M && h->mask[px]) ? W[(size_t)j * h->npix + px] : 0.0;
+                        }
+            }
+            ok = ok && cudaMalloc(&h->d_Wf, Wf.size() * 8) == cudaSuccess && cudaMalloc(&h->d_ginfo, ginfo.size() * 4 + 16) == cudaSuccess;
+            ok = ok && cudaMemcpy(h->d_Wf, Wf.data(), Wf.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && cudaMemcpy(h->d_ginfo, ginfo.data(), ginfo.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
     h->cap_frames = (size_t)max_frames;
     ok = ok && cudaMalloc(&h->d_frames, h->cap_frames * h->npix * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_coef, h->cap_frames * M * 8) == cudaSuccess;
@@ -187,6 +408,9 @@ void zmf_destroy(zmf_handle *h)
     cudaSetDevice(h->device);
     if (h->d_W) cudaFree(h->d_W);
     if (h->d_mask) cudaFree(h->d_mask);
+    if (h->d_Wf) cudaFree(h->d_Wf);
+    if (h->d_ginfo) cudaFree(h->d_ginfo);
+    if (h->d_part) cudaFree(h->d_part);
     if (h->d_frames) cudaFree(h->d_frames);
     if (h->d_coef) cudaFree(h->d_coef);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -217,10 +441,64 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
     if (!h || !frames || !coef) return FMPC_ERR_NULL;
     if (nframes <= 0) return nframes < 0 ? FMPC_ERR_DIM : FMPC_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return FMPC_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->d_Wf && ((uintptr_t)frames & 15) == 0) {
+        // ---- DMMA path: frame-block size and split-K chosen so that the grid holds >= ~6 units per SM ----
+        const int mt = (nframes > 4096) ? 2 : 1;
+        const int fblocks = (nframes + 64 * mt - 1) / (64 * mt);
+        constexpr int CHmin = 8;
+        int ksplit = (6 * h->sm_count + fblocks - 1) / fblocks;
+        if (ksplit > 16) ksplit = 16;
+        const int maxsplit = (h->ngroups + 4 * CHmin - 1) / (4 * CHmin);      // keep >= 4 chunks per split
+        if (ksplit > maxsplit) ksplit = maxsplit;
+        if (ksplit < 1) ksplit = 1;
+        int gps = (h->ngroups + ksplit - 1) / ksplit;
+        gps = (gps + 15) & ~15;                                               // whole shared-memory chunks
+        ksplit = (h->ngroups + gps - 1) / gps;
+        const int ld = 8 * h->ntiles;
+        double *out = coef;
+        int out_ld = h->nmodes;
+        size_t stride = 0;
+        if (ksplit > 1) {
+            stride = (size_t)nframes * ld;
+            const size_t need = stride * ksplit;
+            if (need > h->part_doubles) {
+                if (h->d_part) cudaFree(h->d_part);
+                h->d_part = nullptr; h->part_doubles = 0;
+                if (cudaMalloc(&h->d_part, need * 8) != cudaSuccess) return FMPC_ERR_CUDA;
+                h->part_doubles = need;
+            }
+            out = h->d_part; out_ld = ld;
+        }
+        cudaError_t e = cudaErrorInvalidValue;
+        switch (h->ntiles) {
+        case 1: e = zmf_launch_nt<1>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 2: e = zmf_launch_nt<2>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 3: e = zmf_launch_nt<3>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 4: e = zmf_launch_nt<4>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 5: e = zmf_launch_nt<5>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 6: e = zmf_launch_nt<6>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 7: e = zmf_launch_nt<7>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 8: e = zmf_launch_nt<8>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 9: e = zmf_launch_nt<9>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        default: break;
+        }
+        if (e != cudaSuccess) return FMPC_ERR_CUDA;
+        h->launches += 1;
+        if (ksplit > 1) {
+            const size_t tot = (size_t)nframes * h->nmodes;
+            int rg = (int)((tot + 255) / 256);
+            if (rg > h->sm_count * 8) rg = h->sm_count * 8;
+            zmf_reduce_kernel<<<rg, 256, 0, st>>>(h->d_part, ksplit, stride, ld, coef, h->nmodes, nframes);
+            if (cudaGetLastError() != cudaSuccess) return FMPC_ERR_CUDA;
+            h->launches += 1;
+        }
+        return FMPC_OK;
+    }
+    // generic path (odd frame sizes, > 72 modes): scalar FMA kernel
     constexpr int MC = 7, FT = 4, NT = 256;
     const int grid = (nframes + FT - 1) / FT;
-    zmf_fit_kernel<MC, FT, NT><<<grid, NT, 0, stream ? (cudaStream_t)stream : h->stream>>>(h->d_W, h->d_mask, frames, coef, h->npix,
-                                                                                          h->nmodes, nframes);
+    zmf_fit_kernel<MC, FT, NT><<<grid, NT, 0, st>>>(h->d_W, h->d_mask, frames, coef, h->npix, h->nmodes, nframes);
     if (cudaGetLastError() != cudaSuccess) return FMPC_ERR_CUDA;
     h->launches += 1;
     return FMPC_OK;

@@ -66,3 +66,24 @@ def test_function_mirror(pk):
     assert relerr(ad, ad_ref) < TOL and np.array_equal(nm, nm_ref)
     with pytest.raises(ValueError, match="between 0 and 1"):
         pk.zernmodfit(r * 2, th, d, 4)
+
+
+@pytest.mark.parametrize("nL,N,nf", [(128, 6, 1), (128, 6, 9), (128, 10, 70), (64, 2, 130), (128, 6, 4500), (20, 11, 33), (50, 4, 17)])
+def test_dmma_path_shapes(pk, nL, N, nf):
+    """Every tile-count / frame-tile / split-K configuration of the DMMA kernel (and, for nL % 4 != 0 or > 72 modes,
+    the scalar kernel) against W = pinv(Z) applied in numpy (the oracle's QR route == pinv route, test_oracle_zernike)."""
+    zf = pk.ZernikeFitter(nL, N, max_frames=nf)
+    r, th, is_in = zr.pupil_grid(nL)
+    n_, m_ = zr.mode_indices(N)
+    Z = zr.zernfun(n_, m_, r, th)
+    rs = np.random.RandomState(nL + N + nf)
+    vals = rs.randn(nf, Z.shape[0])
+    frames = np.full((nf, nL * nL), np.nan)
+    frames[:, is_in.T.reshape(-1)] = vals
+    frames = frames.reshape(nf, nL, nL).transpose(0, 2, 1)
+    coef, _ = zf.fit(frames)
+    ref = np.linalg.lstsq(Z, vals.T, rcond=None)[0].T
+    assert np.isfinite(coef).all() and relerr(coef, ref) < TOL
+    if nf <= 70:
+        assert relerr(coef, zr.fit_frames_literal(frames, N)) < TOL
+    zf.close()
