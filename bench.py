@@ -64,6 +64,13 @@ def cpu_port_rate(p, sets, nsample, nthreads=0, reps=1):
     return nb / dt, int(out["iters"].sum()), nb, dt
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -118,12 +125,12 @@ def run_reference(args, rank, world):
     from mpc_sensorlessao_b200 import synth
     from oracle import fmpc_ref
     p = synth.make_problem(N_ZERN, T_HOR)
-    nsample = 512
+    nsample = 2048
     sets = [synth.warm_inputs(p, nsample, seed=100)]
-    cores = fmpc_ref.max_threads()
+    cores = host_threads()          # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     if args.warmup > 0:
-        cpu_port_rate(p, sets, nsample, reps=args.warmup)                      # W untimed warm-up steps
-    rate, it1, nb, dt1 = cpu_port_rate(p, sets, nsample, reps=max(args.steps, 1))   # K timed steps (mean)
+        cpu_port_rate(p, sets, nsample, nthreads=cores, reps=args.warmup)                      # W untimed warm-up steps
+    rate, it1, nb, dt1 = cpu_port_rate(p, sets, nsample, nthreads=cores, reps=max(args.steps, 1))   # K timed steps (mean)
     line = {"impl": "reference", "metric": "fastmpc_solves_per_sec", "value": rate, "unit": "solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt1 * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_desc(),
@@ -267,6 +274,14 @@ def main():
 
     if rank == 0:
         F = f_newton(n, m, T)
+        kname = {2: "fmpc_solve_kernel_warp<28,4>", 1: "fmpc_solve_kernel_mma<28>", 0: "fmpc_solve_kernel_v1"}.get(hb.kernel_kind, "?")
+        traffic = None      # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/)
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if kname in tj and nb == NB_PER_GPU:
+                traffic = float(tj[kname]["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
         solves = nb * K * world
         value = solves / (total_ms_max * 1e-3)
         # roofline of the (single) solve kernel: algorithmic flops of one launch / its average duration
@@ -282,8 +297,8 @@ def main():
                     "api": "fmpc_step (C-ABI, pinned host buffers)"},
             "gpu_launches": launches_all,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)",
-                         "kernel": {2: "fmpc_solve_kernel_warp<28,4>", 1: "fmpc_solve_kernel_mma<28>", 0: "fmpc_solve_kernel_v1"}.get(hb.kernel_kind, "?"), "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": kname, "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
                          "peak_source": "measured live: fmpc_fp64_peak DMMA m8n8k4 %.2f / DFMA %.2f TFLOP/s "
                                         "(MEASURED_PEAKS.json has no FP64 entry)" % (peak_dmma, peak_dfma),
                          "flops_per_newton_iter": F, "newton_iters_per_launch": newton_iters / K, "kernel_ms": kern_ms},
@@ -291,13 +306,15 @@ def main():
             "aggregate_tflops": newton_iters_all * F / (total_ms_max * 1e-3) / 1e12,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            nsample = 2048
-            rate, it, nbs, dt = cpu_port_rate(p, sets, nsample, reps=3)
-            from oracle import fmpc_ref
-            line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": fmpc_ref.max_threads(), "kind": "port",
-                                    "sample": f"{nbs} of the {nb} instances, 3 repetitions ({3 * dt:.1f} s), structured C/OpenMP port "
-                                              "(oracle/fmpc_ref.c); the MATLAB reference cannot run on this box"}
+            cores = host_threads()
+            nsample = nb
+            r0, _, _, dt0 = cpu_port_rate(p, sets, nsample, nthreads=cores, reps=1)
+            reps = max(3, min(60, int(round(12.0 / max(dt0, 1e-3)))))          # ~12 s of CPU work
+            rate, it, nbs, dt = cpu_port_rate(p, sets, nsample, nthreads=cores, reps=reps)
+            line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                                    "sample": f"all {nbs} instances of one step, {reps} repetitions ({reps * dt:.1f} s), structured "
+                                              "C/OpenMP port (oracle/fmpc_ref.c) on every host thread; the MATLAB reference cannot "
+                                              "run on this box"}
         print(json.dumps(line), flush=True)
     hb.close()
     if world > 1:

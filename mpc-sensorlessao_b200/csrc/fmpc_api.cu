@@ -87,8 +87,9 @@ struct fmpc_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // host-buffer entry points: copy-in / solve / copy-out of successive instance chunks overlap on three streams
-    static constexpr int MAX_CHUNKS = 8;
+    static constexpr int MAX_CHUNKS = 32, MAX_PART = 4;
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_k[MAX_PART] = {};      // solve streams: partition p of the SMs / scratch slots runs chunks p, p + NP, ...
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     std::vector<void *> sys_allocs;       // problem-constant device arrays
     DevBuf ws, counters;                  // per-CTA scratch; {counter u32 (pad), iters_total u64}
@@ -283,6 +284,7 @@ void fmpc_destroy(fmpc_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < fmpc_handle::MAX_CHUNKS; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
+    for (int i = 0; i < fmpc_handle::MAX_PART; ++i) if (h->s_k[i]) cudaStreamDestroy(h->s_k[i]);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -384,7 +386,8 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     if (ok) {
         h->ws_stride = h->cfg.ws_stride;
         const size_t wsb = (size_t)h->cfg.slots * h->cfg.ws_stride * sizeof(double);
-        if (h->ws.ensure(wsb) || h->counters.ensure(256)) ok = false;
+        if (h->ws.ensure(wsb) || h->counters.ensure(256 * fmpc_handle::MAX_PART)) ok = false;
+        if (ok && cudaMemset(h->counters.p, 0, 256 * fmpc_handle::MAX_PART) != cudaSuccess) ok = false;
         // the warp kernel relies on never-written padding columns of its scratch staying zero
         if (ok && cudaMemset(h->ws.p, 0, wsb) != cudaSuccess) ok = false;
     }
@@ -392,6 +395,8 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     if (ok && (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)) ok = false;
     if (ok && (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess ||
                cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess)) ok = false;
+    for (int i = 0; ok && i < fmpc_handle::MAX_PART; ++i)
+        if (cudaStreamCreateWithFlags(&h->s_k[i], cudaStreamNonBlocking) != cudaSuccess) ok = false;
     for (int i = 0; ok && i < fmpc_handle::MAX_CHUNKS; ++i)
         if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
@@ -429,13 +434,19 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
     cudaSetDevice(h->device);
     unsigned long long v = 0;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
-    if (cudaMemcpy(&v, h->counters.as<char>() + 8, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int p = 0; p < fmpc_handle::MAX_PART; ++p) {
+        unsigned long long vp = 0;
+        if (cudaStreamSynchronize(h->s_k[p]) != cudaSuccess) return -1;
+        if (cudaMemcpy(&vp, h->counters.as<char>() + 256 * p + 8, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        v += vp;
+    }
     return (long long)v;
 }
 
 static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
                        const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
-                       double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false)
+                       double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false,
+                       int part = 0, int nparts = 1)
 {
     StepArgs A{};
     A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
@@ -443,15 +454,21 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     A.alpha = p->alpha; A.beta = p->beta; A.tol_r = p->tol_r; A.tol_p = p->tol_p;
     A.x0 = x0; A.x0_pre = x0_pre; A.u_prev = u_prev; A.w = w; A.xf = xf; A.X0 = X0; A.U0 = U0; A.nu0 = nu0;
     A.X = X; A.U = U; A.status = status; A.iters = iters;
-    A.counter = h->counters.as<unsigned int>();
-    A.iters_total = (unsigned long long *)(h->counters.as<char>() + 8);
+    // partition `part` of `nparts`: its own counter block, a disjoint range of CTA slots (scratch) and a grid of that size
+    char *cblk = h->counters.as<char>() + 256 * part;
+    A.counter = (unsigned int *)cblk;
+    A.iters_total = (unsigned long long *)(cblk + 8);
+    SolveLaunchCfg cfg = h->cfg;
+    if (nparts > 1) { cfg.grid = h->cfg.grid / nparts; A.slot_base = part * cfg.grid; }
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     A.prof = (long long *)(h->counters.as<char>() + 64);
-    CU_OK(cudaMemsetAsync(h->counters.p, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
+    CU_OK(cudaMemsetAsync(cblk, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
+    if (!keep_totals && nparts == 1 && part == 0)                    // a whole-grid launch starts a new total: clear the other partitions'
+        CU_OK(cudaMemsetAsync(h->counters.as<char>() + 256, 0, 256 * (fmpc_handle::MAX_PART - 1), st));
     if (h->cfg.use_mma == 3) {
         if (nbatch > h->max_batch) return FMPC_ERR_BATCH;     // its scratch is sized by max_batch
         fmpc_launch_solve_gen(h->S, h->G, A, h->cfg, st);
-    } else if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, h->cfg, st);
+    } else if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, cfg, st);
     else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
     else fmpc_launch_solve(h->S, A, h->cfg, st);
     CU_OK(cudaGetLastError());
@@ -504,42 +521,54 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
         for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
         nu_src = h->h_nu.data();
     }
-    // Instances are independent: the batch is cut into chunks of about one launch wave each, and copy-in (s_in),
-    // solve (st) and copy-out (s_out) of successive chunks overlap.  With pageable host memory the copies degrade to
+    // Instances are independent: the batch is cut into chunks, and copy-in (s_in), solve and copy-out (s_out) of successive
+    // chunks overlap.  The warp kernel additionally splits the SMs (and its per-slot scratch) into NP partitions, each with its
+    // own solve stream: chunk c runs as one wave on partition c % NP, so NP chunk kernels are resident side by side and the
+    // pipeline fill / drain is a 1/NP-wave chunk instead of a whole wave.  With pageable host memory the copies degrade to
     // staged synchronous ones; the results are the same.
-    int nch = (int)((nb + (size_t)h->cfg.slots / 2) / (size_t)h->cfg.slots);
-    if (nch < 1) nch = 1;
-    if (nch > fmpc_handle::MAX_CHUNKS) nch = fmpc_handle::MAX_CHUNKS;
-    const size_t per = (nb + nch - 1) / nch;
+    int NP = 1;
+    // measured (profiles/r01_v3_7_e2e_partitions.log): 2 partitions beat 1 and 4 -- the host->device copies of a step
+    // (133 MB at C2) take nearly as long as its solves, so finer chunks only add per-copy overhead
+    if (h->cfg.use_mma == 2 && h->cfg.grid >= 4 * fmpc_handle::MAX_PART && nb > (size_t)h->cfg.slots / 2) NP = 2;
+    if (const char *e = getenv("FMPC_STEP_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= fmpc_handle::MAX_PART && h->cfg.use_mma == 2) NP = v; }
+    const size_t wave = (NP > 1) ? (size_t)(h->cfg.grid / NP) * (size_t)(h->cfg.block / 32) : (size_t)h->cfg.slots;
+    size_t per = wave;
+    int nch = (int)((nb + per - 1) / per);
+    if (NP == 1) { nch = (int)((nb + wave / 2) / wave); if (nch < 1) nch = 1; }
+    while (nch > fmpc_handle::MAX_CHUNKS) { per += wave; nch = (int)((nb + per - 1) / per); }
+    if (NP == 1) per = (nb + nch - 1) / nch;
     cudaStream_t si = h->s_in, so = h->s_out;
     const size_t Tn = (size_t)T * n, Tm = (size_t)T * m;
     while (nch > 1 && (size_t)(nch - 1) * per >= nb) --nch;           // no empty trailing chunk
+    // the per-instance vectors are small: one copy each for the whole batch, ahead of the chunked arrays
+    CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, si));
+    if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, si));
+    if (u_prev && h->ramp) CU_OK(cudaMemcpyAsync(h->d_uprev.p, u_prev, nb * m * 8, cudaMemcpyHostToDevice, si));
+    if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.p, xf, nb * n * 8, cudaMemcpyHostToDevice, si));
     // enqueue order per chunk: copy-in(ci), solve(ci), copy-out(ci-1) -- so that even blocking (pageable) copies
     // leave the solve of the current chunk running underneath them
     for (int ci = 0; ci <= nch; ++ci) {
         if (ci < nch) {
             const size_t b0 = (size_t)ci * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
-            CU_OK(cudaMemcpyAsync(h->d_x0.as<double>() + b0 * n, x0 + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
-            if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.as<double>() + b0 * n, x0_pre + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
-            if (u_prev && h->ramp) CU_OK(cudaMemcpyAsync(h->d_uprev.as<double>() + b0 * m, u_prev + b0 * m, cb * m * 8, cudaMemcpyHostToDevice, si));
+            const int part = ci % NP;
+            cudaStream_t sk = (NP > 1) ? h->s_k[part] : st;
             if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, w + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
-            if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.as<double>() + b0 * n, xf + b0 * n, cb * n * 8, cudaMemcpyHostToDevice, si));
             if (X0) {
                 CU_OK(cudaMemcpyAsync(h->d_X.as<double>() + b0 * Tn, X0 + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
                 CU_OK(cudaMemcpyAsync(h->d_U.as<double>() + b0 * Tm, U0 + b0 * Tm, cb * Tm * 8, cudaMemcpyHostToDevice, si));
             }
             CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + b0 * NBn, nu_src + b0 * NBn, cb * NBn * 8, cudaMemcpyHostToDevice, si));
             CU_OK(cudaEventRecord(h->ev_in[ci], si));
-            CU_OK(cudaStreamWaitEvent(st, h->ev_in[ci], 0));
-            if (ci == 0) CU_OK(cudaEventRecord(h->ev0, st));
+            CU_OK(cudaStreamWaitEvent(sk, h->ev_in[ci], 0));
+            if (ci == 0) CU_OK(cudaEventRecord(h->ev0, sk));
             rc = step_device(h, p, (int)cb, h->d_x0.as<double>() + b0 * n, x0_pre ? h->d_x0pre.as<double>() + b0 * n : nullptr,
                              (u_prev && h->ramp) ? h->d_uprev.as<double>() + b0 * m : nullptr, w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
                              X0 ? h->d_X.as<double>() + b0 * Tn : nullptr, X0 ? h->d_U.as<double>() + b0 * Tm : nullptr,
                              h->d_nu0.as<double>() + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
-                             h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, st, ci > 0);
+                             h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, sk, ci >= NP, part, NP);
             if (rc) return rc;
-            CU_OK(cudaEventRecord(h->ev_k[ci], st));
-            if (ci == nch - 1) CU_OK(cudaEventRecord(h->ev1, st));
+            CU_OK(cudaEventRecord(h->ev_k[ci], sk));
+            if (NP > 1) CU_OK(cudaStreamWaitEvent(st, h->ev_k[ci], 0));      // st collects every chunk (ev1, final sync)
         }
         if (ci >= 1) {
             const int cj = ci - 1;
@@ -547,10 +576,11 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
             CU_OK(cudaStreamWaitEvent(so, h->ev_k[cj], 0));
             CU_OK(cudaMemcpyAsync(X + b0 * Tn, h->d_X.as<double>() + b0 * Tn, cb * Tn * 8, cudaMemcpyDeviceToHost, so));
             CU_OK(cudaMemcpyAsync(U + b0 * Tm, h->d_U.as<double>() + b0 * Tm, cb * Tm * 8, cudaMemcpyDeviceToHost, so));
-            if (status) CU_OK(cudaMemcpyAsync(status + b0, h->d_status.as<int>() + b0, cb * 4, cudaMemcpyDeviceToHost, so));
-            if (iters) CU_OK(cudaMemcpyAsync(iters + b0, h->d_iters.as<int>() + b0, cb * 4, cudaMemcpyDeviceToHost, so));
         }
     }
+    if (status) CU_OK(cudaMemcpyAsync(status, h->d_status.p, nb * 4, cudaMemcpyDeviceToHost, so));
+    if (iters) CU_OK(cudaMemcpyAsync(iters, h->d_iters.p, nb * 4, cudaMemcpyDeviceToHost, so));
+    CU_OK(cudaEventRecord(h->ev1, st));
     CU_OK(cudaStreamSynchronize(so));
     CU_OK(cudaStreamSynchronize(st));
     CU_OK(cudaStreamSynchronize(si));

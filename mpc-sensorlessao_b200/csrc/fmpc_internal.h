@@ -45,6 +45,7 @@ struct StepArgs {
     unsigned long long *iters_total;    // sum of Newton iterations (zeroed before launch)
     double *ws;                         // per-slot scratch (slot = CTA for the CTA kernels, warp for the warp kernel)
     size_t ws_stride;                   // doubles per slot
+    int slot_base;                      // first CTA-slot of this launch (concurrent launches of one handle use disjoint slot ranges)
     long long *prof;                    // optional phase-cycle accumulators (builds with -DFMPC_PROF), else NULL
 };
 

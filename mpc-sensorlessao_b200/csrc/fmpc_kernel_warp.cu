@@ -1255,7 +1255,7 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
     c.kappa = A.kappa;
     c.smem = smem; c.oA1 = (int)(sA1 - smem); c.oA2 = (int)(sA2 - smem); c.oU = (int)(sUmax - smem); c.oQ = (int)(sQ2 - smem);
     c.wsm = smem + G.const_doubles + (size_t)wid * G.warp_doubles; c.BLK = G.BLK;
-    double *ws = A.ws + ((size_t)blockIdx.x * nwarps + wid) * A.ws_stride;
+    double *ws = A.ws + ((size_t)(A.slot_base + blockIdx.x) * nwarps + wid) * A.ws_stride;
     c.ws = ws; c.tu = G.TP8 * G.mpad; c.tx = G.TP8 * npad; c.tb = (G.TP8 + 1) * npad; c.bl = (T + 1) * G.NN; c.pp = 0;
     c.ypool = S.ypool; c.ydi = S.ydi; c.y1i = S.y1i; c.y2i = S.y2i;
     c.xmin = S.xmin; c.xmax = S.xmax;

@@ -129,6 +129,10 @@ namespace {
 
 constexpr int ZSTAGES = 3;
 template <int NT> struct ZChunk { static constexpr int CH = (NT <= 4) ? 16 : 8; };     // groups per shared-memory stage
+#ifndef ZMF_PF
+#define ZMF_PF 16
+#endif
+constexpr int ZPF = ZMF_PF;                                                           // L2 prefetch distance (groups), 0 = off
 constexpr int ZRING = 4;                                                             // frame-load ring depth (groups)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -183,17 +187,20 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
+    // register ring: frame data of the next ZRING groups, group descriptors of the next 2 ZRING groups (so that the
+    // address of a frame load never waits on the descriptor load in front of it)
     double2 ring[ZRING][MT];
-    unsigned rinfo[ZRING];
-    auto load = [&](int d, int g) {
-        const unsigned info = __ldg(ginfo + min(g, ngroups - 1));
-        rinfo[d] = info;
+    unsigned rinfo[ZRING], ninfo[ZRING];
+    auto load_info = [&](int g) { return __ldg(ginfo + min(g, ngroups - 1)); };
+    auto load_frames = [&](int d, unsigned info) {
         const size_t off = (size_t)(info & 0xFFFFFFu) * 8;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) ring[d][mt] = __ldcs(reinterpret_cast<const double2 *>(fr[mt] + off));
     };
 #pragma unroll
-    for (int d = 0; d < ZRING; ++d) load(d, g_begin + d);
+    for (int d = 0; d < ZRING; ++d) { rinfo[d] = load_info(g_begin + d); ninfo[d] = load_info(g_begin + ZRING + d); }
+#pragma unroll
+    for (int d = 0; d < ZRING; ++d) load_frames(d, rinfo[d]);
 
     for (int c = 0; c < nch; ++c) {
         const int s = c % ZSTAGES;
@@ -203,6 +210,16 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
         const int g0 = g_begin + c * CH;
 #pragma unroll 1
         for (int gi = 0; gi < CH; gi += ZRING) {
+            // DRAM -> L2 prefetch, ZPF groups ahead: lane l < 8 MT owns frame row f0 + l and pulls the 128-byte lines of
+            // the next 4 groups of that frame in one burst (neighbouring lines of one DRAM page arrive together)
+            if (ZPF > 0 && lane < 8 * MT) {
+                const double *row = frames + (size_t)min(f0 + lane, nframes - 1) * npix;
+#pragma unroll
+                for (int d = 0; d < ZRING; d += 2) {
+                    const unsigned pi = __ldg(ginfo + min(g0 + gi + ZPF + d, ngroups - 1));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (size_t)(pi & 0xFFFFFFu) * 8));
+                }
+            }
 #pragma unroll
             for (int d = 0; d < ZRING; ++d) {
                 const int g = g0 + gi + d;
@@ -218,14 +235,22 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
                             if (!((mk >> (2 * q + 1)) & 1u)) av[mt].y = 0.0;
                         }
                     }
-                    load(d, g + ZRING);
+                    rinfo[d] = ninfo[d];
+                    load_frames(d, rinfo[d]);            // group g + ZRING
+                    ninfo[d] = load_info(g + 2 * ZRING);
                     const double *wg = wb + (size_t)(gi + d) * GD;
+                    double2 b[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const double2 b = *reinterpret_cast<const double2 *>(wg + nt * 64);
+                    for (int nt = 0; nt < NT; ++nt) b[nt] = *reinterpret_cast<const double2 *>(wg + nt * 64);
+                    // all first k-steps, then all second k-steps: NT * MT independent DMMAs between dependent ones
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) { zdmma(acc[mt][nt], av[mt].x, b.x); zdmma(acc[mt][nt], av[mt].y, b.y); }
-                    }
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) zdmma(acc[mt][nt], av[mt].x, b[nt].x);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) zdmma(acc[mt][nt], av[mt].y, b[nt].y);
                 }
             }
         }
