@@ -228,6 +228,20 @@ int zmf_get_basis(const zmf_handle *h, double *Z);
 int zmf_get_mask(const zmf_handle *h, unsigned char *mask);
 long long zmf_launch_count(const zmf_handle *h);
 
+/* ======================================================================================= */
+/* Estimator step in front of the solve (README.md:478):                                      */
+/*     ad_est = lsqminnorm((A_s'*A_s), ((A_s)'*(Y_M - b_s)));                                 */
+/* with A_s (npix x nmodes, column-major; the caller removes the piston column like           */
+/* README.md:289-290) and b_s (npix) from model_approx.mat.  Batched: y is npix x nb (one      */
+/* measurement vector Y_M per column), x_hat is nmodes x nb.  b_s may be NULL (zeros).         */
+/* FMPC_ERR_NOT_PD if A_s is rank deficient (lsqminnorm's minimum-norm branch is not covered). */
+typedef struct zmf_handle est_handle;
+int est_create(est_handle **out, int npix, int nmodes, const double *A_s, const double *b_s, int max_batch, int device);
+void est_destroy(est_handle *h);
+int est_apply(est_handle *h, int nb, const double *y, double *x_hat, double *telapsed);          /* HOST buffers */
+int est_apply_d(est_handle *h, int nb, const double *y, double *x_hat, void *stream);            /* DEVICE buffers */
+long long est_launch_count(const est_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

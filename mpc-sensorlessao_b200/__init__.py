@@ -3,6 +3,7 @@
 Host-side mirror (Python, ctypes) of the reference's MATLAB interface for this path:
   Fast_MPC2 / Fast_MPC2_VAR1  <->  Fast_MPC/VAR_2/Fast_MPC2.m, Fast_MPC/VAR_1/Fast_MPC2.m
   zernmodfit / ZernikeFitter  <->  zernmodfit.m (+ zernfun.m)
+  Estimator                   <->  the lsqminnorm estimator step, README.md:478 (model_approx.mat)
   FastMPCBatch                 :   the batched C-ABI (include/fmpc.h) for many instances
 All compute runs in the CUDA library `lib/libfmpc_b200.so`; there is no CPU fallback.
 """
@@ -10,7 +11,8 @@ from ._lib import (FmpcError, FmpcParams, build_library, device_count, fp64_peak
                    strerror)
 from .fast_mpc2 import FastMPCBatch, Fast_MPC2, Fast_MPC2_VAR1, deinterleave, interleave
 from .zernike import ZernikeFitter, zernmodfit
+from .estimator import Estimator
 
 __all__ = ["FmpcError", "FmpcParams", "build_library", "device_count", "fp64_peak", "lib_path", "load_library",
            "strerror", "FastMPCBatch", "Fast_MPC2", "Fast_MPC2_VAR1", "deinterleave", "interleave",
-           "ZernikeFitter", "zernmodfit"]
+           "ZernikeFitter", "zernmodfit", "Estimator"]

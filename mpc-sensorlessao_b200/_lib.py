@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
     "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
+    "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count",
 ]
 
 
@@ -91,7 +92,12 @@ def load_library():
     L.fmpc_state_update.argtypes = [vp, C.c_int] + [vp] * 5
     L.fmpc_state_update_d.argtypes = [vp, C.c_int] + [vp] * 6
     L.fmpc_closed_loop.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6
-    for f in ("fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "zmf_launch_count"):
+    L.est_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]
+    L.est_destroy.argtypes = [vp]
+    L.est_destroy.restype = None
+    L.est_apply.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.est_apply_d.argtypes = [vp, C.c_int, vp, vp, vp]
+    for f in ("fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "zmf_launch_count", "est_launch_count"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = C.c_longlong
     L.fmpc_kernel_kind.argtypes = [vp]

@@ -61,6 +61,7 @@ struct zmf_handle {
     double *d_Wf = nullptr;                // [group][ntile][lane][2] fragment-ordered W
     unsigned *d_ginfo = nullptr;           // per group: (first pixel / 8) | (pixel mask << 24)
     int ngroups = 0, ntiles = 0;
+    double *d_off = nullptr;               // nmodes: constant subtracted from every output column (estimator: W b_s), or NULL
     double *d_part = nullptr;              // split-K partial sums [ksplit][nframes][8 ntiles]
     size_t part_doubles = 0;
     int sm_count = 148;
@@ -77,7 +78,7 @@ struct zmf_handle {
 template <int MC, int FT, int NT>
 __global__ void __launch_bounds__(NT) zmf_fit_kernel(const double *__restrict__ W, const unsigned char *__restrict__ mask,
                                                      const double *__restrict__ frames, double *__restrict__ coef,
-                                                     int npix, int nmodes, int nframes)
+                                                     int npix, int nmodes, int nframes, const double *__restrict__ off)
 {
     __shared__ double red[NT / 32][MC * FT];
     const int f0 = blockIdx.x * FT;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NT) zmf_fit_kernel(const double *__restrict__ 
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w) v += red[w][tid];
             const int a = tid / FT, b = tid % FT;
-            if (j0 + a < nmodes && f0 + b < nframes) coef[(size_t)(f0 + b) * nmodes + j0 + a] = v;
+            if (j0 + a < nmodes && f0 + b < nframes) coef[(size_t)(f0 + b) * nmodes + j0 + a] = off ? v - off[j0 + a] : v;
         }
         __syncthreads();
     }
@@ -148,11 +149,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
     return ok != 0;
 }
 
-template <int NT, int MT, int NW>
+template <int NT, int MT, int NW, bool VEC>
 __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__restrict__ Wf, const unsigned *__restrict__ ginfo, int ngroups,
                                                                int groups_per_split, const double *__restrict__ frames,
                                                                double *__restrict__ out, int out_ld, size_t out_split_stride,
-                                                               int npix, int nmodes, int nframes)
+                                                               int npix, int nmodes, int nframes, const double *__restrict__ offv)
 {
     constexpr int CH = ZChunk<NT>::CH, GD = NT * 64;            // doubles of W per group
     extern __shared__ __align__(128) double wbuf[];             // ZSTAGES x CH x GD
@@ -194,8 +195,18 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
     auto load_info = [&](int g) { return __ldg(ginfo + min(g, ngroups - 1)); };
     auto load_frames = [&](int d, unsigned info) {
         const size_t off = (size_t)(info & 0xFFFFFFu) * 8;
+        if (VEC) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) ring[d][mt] = __ldcs(reinterpret_cast<const double2 *>(fr[mt] + off));
+            for (int mt = 0; mt < MT; ++mt) ring[d][mt] = __ldcs(reinterpret_cast<const double2 *>(fr[mt] + off));
+        } else {        // rows that are not 16-byte aligned (odd row length): two scalar loads, never past the end of a row
+            const unsigned mk = info >> 24;
+            const bool p0 = (mk >> (2 * q)) & 1u, p1 = (mk >> (2 * q + 1)) & 1u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                ring[d][mt].x = p0 ? __ldcs(fr[mt] + off) : 0.0;
+                ring[d][mt].y = p1 ? __ldcs(fr[mt] + off + 1) : 0.0;
+            }
+        }
     };
 #pragma unroll
     for (int d = 0; d < ZRING; ++d) { rinfo[d] = load_info(g_begin + d); ninfo[d] = load_info(g_begin + ZRING + d); }
@@ -270,7 +281,8 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int j = 8 * nt + 2 * q + e;
-                    if (j < out_ld && (out_ld != nmodes || j < nmodes)) o[(size_t)f * out_ld + j] = acc[mt][nt][e];
+                    if (j < out_ld && (out_ld != nmodes || j < nmodes))
+                        o[(size_t)f * out_ld + j] = (offv && j < nmodes) ? acc[mt][nt][e] - offv[j] : acc[mt][nt][e];
                 }
         }
     }
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
 
 // coef[f][j] = sum over splits of part[split][f][j]   (fixed order: deterministic)
 __global__ void zmf_reduce_kernel(const double *__restrict__ part, int ksplit, size_t split_stride, int ld, double *__restrict__ coef,
-                                  int nmodes, int nframes)
+                                  int nmodes, int nframes, const double *__restrict__ offv)
 {
     const size_t tot = (size_t)nframes * nmodes;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
@@ -286,11 +298,11 @@ __global__ void zmf_reduce_kernel(const double *__restrict__ part, int ksplit, s
         const int j = (int)(e - f * nmodes);
         double s = 0.0;
         for (int k = 0; k < ksplit; ++k) s += part[(size_t)k * split_stride + f * ld + j];
-        coef[e] = s;
+        coef[e] = offv ? s - offv[j] : s;
     }
 }
 
-template <int NT, int MT, int NW>
+template <int NT, int MT, int NW, bool VEC>
 cudaError_t zmf_launch_dmma(const zmf_handle *h, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
                             int ksplit, int gps, cudaStream_t st)
 {
@@ -298,13 +310,13 @@ cudaError_t zmf_launch_dmma(const zmf_handle *h, int nframes, const double *fram
     const size_t smem = (size_t)ZSTAGES * CH * NT * 64 * 8;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid((nframes + NW * 8 * MT - 1) / (NW * 8 * MT), ksplit);
-    zmf_fit_dmma_kernel<NT, MT, NW><<<grid, NW * 32, smem, st>>>(h->d_Wf, h->d_ginfo, h->ngroups, gps, frames, out, out_ld, split_stride,
-                                                                 h->npix, h->nmodes, nframes);
+    zmf_fit_dmma_kernel<NT, MT, NW, VEC><<<grid, NW * 32, smem, st>>>(h->d_Wf, h->d_ginfo, h->ngroups, gps, frames, out, out_ld, split_stride,
+                                                                      h->npix, h->nmodes, nframes, ksplit > 1 ? nullptr : h->d_off);
     return cudaGetLastError();
 }
 
@@ -312,11 +324,56 @@ template <int NT>
 cudaError_t zmf_launch_nt(const zmf_handle *h, int mt, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
                           int ksplit, int gps, cudaStream_t st)
 {
-    if (mt == 2) return zmf_launch_dmma<NT, 2, 8>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
-    return zmf_launch_dmma<NT, 1, 8>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    if (mt < 0) return zmf_launch_dmma<NT, 1, 8, false>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    if (mt == 2) return zmf_launch_dmma<NT, 2, 8, true>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    return zmf_launch_dmma<NT, 1, 8, true>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
 }
 
 } // namespace
+
+// Uploads the least-squares operator W (nmodes x npix, row j contiguous over pixels, exact zeros where mask == 0) and
+// builds the DMMA tables; allocates staging for max_frames.  Shared by zmf_create and est_create.
+static bool linfit_upload(zmf_handle *h, const std::vector<double> &W, int sm_count, int max_frames)
+{
+    const int M = h->nmodes;
+    bool ok = cudaMalloc(&h->d_W, W.size() * 8) == cudaSuccess && cudaMalloc(&h->d_mask, h->npix) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_W, W.data(), W.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_mask, h->mask.data(), h->npix, cudaMemcpyHostToDevice) == cudaSuccess;
+    {   // DMMA path tables (<= 72 modes)
+        h->sm_count = sm_count;
+        h->ntiles = (M + 7) / 8;
+        if (h->ntiles <= 9) {
+            std::vector<unsigned> ginfo;
+            for (int g = 0; g < (h->npix + 7) / 8; ++g) {
+                unsigned mk = 0;
+                for (int e = 0; e < 8; ++e) if ((size_t)8 * g + e < (size_t)h->npix && h->mask[(size_t)8 * g + e]) mk |= 1u << e;
+                if (mk) ginfo.push_back((unsigned)g | (mk << 24));
+            }
+            h->ngroups = (int)ginfo.size();
+            const int NTl = h->ntiles;
+            std::vector<double> Wf((size_t)h->ngroups * NTl * 64, 0.0);
+            for (int gi = 0; gi < h->ngroups; ++gi) {
+                const size_t p0 = (size_t)(ginfo[gi] & 0xFFFFFFu) * 8;
+                for (int nt = 0; nt < NTl; ++nt)
+                    for (int ln = 0; ln < 32; ++ln)
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = 8 * nt + (ln >> 2);
+                            const size_t px = p0 + 2 * (ln & 3) + e;
+                            Wf[(((size_t)gi * NTl + nt) * 32 + ln) * 2 + e] = (j < M && px < (size_t)h->npix && h->mask[px]) ? W[(size_t)j * h->npix + px] : 0.0;
+                        }
+            }
+            ok = ok && cudaMalloc(&h->d_Wf, Wf.size() * 8) == cudaSuccess && cudaMalloc(&h->d_ginfo, ginfo.size() * 4 + 16) == cudaSuccess;
+            ok = ok && cudaMemcpy(h->d_Wf, Wf.data(), Wf.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && cudaMemcpy(h->d_ginfo, ginfo.data(), ginfo.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    h->cap_frames = (size_t)max_frames;
+    ok = ok && cudaMalloc(&h->d_frames, h->cap_frames * h->npix * 8) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_coef, h->cap_frames * M * 8) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    return ok;
+}
 
 extern "C" {
 
@@ -386,42 +443,7 @@ int zmf_create(zmf_handle **out, int nL, int N, int max_frames, int device)
         for (int j = M - 1; j >= 0; --j) { long double s = col[j]; for (int k = j + 1; k < M; ++k) s -= G[(size_t)k * M + j] * col[k]; col[j] = s / G[(size_t)j * M + j]; }
         for (int j = 0; j < M; ++j) W[(size_t)j * h->npix + pidx[p]] = (double)col[j];
     }
-    bool ok = cudaMalloc(&h->d_W, W.size() * 8) == cudaSuccess && cudaMalloc(&h->d_mask, h->npix) == cudaSuccess;
-    ok = ok && cudaMemcpy(h->d_W, W.data(), W.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMemcpy(h->d_mask, h->mask.data(), h->npix, cudaMemcpyHostToDevice) == cudaSuccess;
-    {   // DMMA path tables: needs 16-byte aligned frame rows and whole 8-pixel groups (nL % 4 == 0) and <= 72 modes
-        h->sm_count = prop.multiProcessorCount;
-        h->ntiles = (M + 7) / 8;
-        if (h->npix % 8 == 0 && h->ntiles <= 9) {
-            std::vector<unsigned> ginfo;
-            for (int g = 0; g < h->npix / 8; ++g) {
-                unsigned mk = 0;
-                for (int e = 0; e < 8; ++e) if (h->mask[(size_t)8 * g + e]) mk |= 1u << e;
-                if (mk) ginfo.push_back((unsigned)g | (mk << 24));
-            }
-            h->ngroups = (int)ginfo.size();
-            const int NTl = h->ntiles;
-            std::vector<double> Wf((size_t)h->ngroups * NTl * 64, 0.0);
-            for (int gi = 0; gi < h->ngroups; ++gi) {
-                const size_t p0 = (size_t)(ginfo[gi] & 0xFFFFFFu) * 8;
-                for (int nt = 0; nt < NTl; ++nt)
-                    for (int ln = 0; ln < 32; ++ln)
-                        for (int e = 0; e < 2; ++e) {
-                            const int j = 8 * nt + (ln >> 2);
-                            const size_t px = p0 + 2 * (ln & 3) + e;
-                            Wf[(((size_t)gi * NTl + nt) * 32 + ln) * 2 + e] = (j < M && h->mask[px]) ? W[(size_t)j * h->npix + px] : 0.0;
-                        }
-            }
-            ok = ok && cudaMalloc(&h->d_Wf, Wf.size() * 8) == cudaSuccess && cudaMalloc(&h->d_ginfo, ginfo.size() * 4 + 16) == cudaSuccess;
-            ok = ok && cudaMemcpy(h->d_Wf, Wf.data(), Wf.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-            ok = ok && cudaMemcpy(h->d_ginfo, ginfo.data(), ginfo.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-        }
-    }
-    h->cap_frames = (size_t)max_frames;
-    ok = ok && cudaMalloc(&h->d_frames, h->cap_frames * h->npix * 8) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_coef, h->cap_frames * M * 8) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+    const bool ok = linfit_upload(h, W, prop.multiProcessorCount, max_frames);
     if (!ok) { zmf_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
     return FMPC_OK;
@@ -436,6 +458,7 @@ void zmf_destroy(zmf_handle *h)
     if (h->d_Wf) cudaFree(h->d_Wf);
     if (h->d_ginfo) cudaFree(h->d_ginfo);
     if (h->d_part) cudaFree(h->d_part);
+    if (h->d_off) cudaFree(h->d_off);
     if (h->d_frames) cudaFree(h->d_frames);
     if (h->d_coef) cudaFree(h->d_coef);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -467,9 +490,11 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
     if (nframes <= 0) return nframes < 0 ? FMPC_ERR_DIM : FMPC_OK;
     if (cudaSetDevice(h->device) != cudaSuccess) return FMPC_ERR_CUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    if (h->d_Wf && ((uintptr_t)frames & 15) == 0) {
+    if (h->d_Wf) {
         // ---- DMMA path: frame-block size and split-K chosen so that the grid holds >= ~6 units per SM ----
-        const int mt = (nframes > 4096) ? 2 : 1;
+        const bool vec = (h->npix % 8 == 0) && ((uintptr_t)frames & 15) == 0;      // 16-byte aligned rows of whole 8-pixel groups
+        int mt = (nframes > 4096) ? 2 : 1;
+        if (!vec) mt = 1;
         const int fblocks = (nframes + 64 * mt - 1) / (64 * mt);
         constexpr int CHmin = 8;
         int ksplit = (6 * h->sm_count + fblocks - 1) / fblocks;
@@ -496,16 +521,17 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
             out = h->d_part; out_ld = ld;
         }
         cudaError_t e = cudaErrorInvalidValue;
+        const int mtsel = vec ? mt : -1;
         switch (h->ntiles) {
-        case 1: e = zmf_launch_nt<1>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 2: e = zmf_launch_nt<2>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 3: e = zmf_launch_nt<3>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 4: e = zmf_launch_nt<4>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 5: e = zmf_launch_nt<5>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 6: e = zmf_launch_nt<6>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 7: e = zmf_launch_nt<7>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 8: e = zmf_launch_nt<8>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
-        case 9: e = zmf_launch_nt<9>(h, mt, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 1: e = zmf_launch_nt<1>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 2: e = zmf_launch_nt<2>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 3: e = zmf_launch_nt<3>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 4: e = zmf_launch_nt<4>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 5: e = zmf_launch_nt<5>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 6: e = zmf_launch_nt<6>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 7: e = zmf_launch_nt<7>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 8: e = zmf_launch_nt<8>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
+        case 9: e = zmf_launch_nt<9>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
         default: break;
         }
         if (e != cudaSuccess) return FMPC_ERR_CUDA;
@@ -514,7 +540,7 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
             const size_t tot = (size_t)nframes * h->nmodes;
             int rg = (int)((tot + 255) / 256);
             if (rg > h->sm_count * 8) rg = h->sm_count * 8;
-            zmf_reduce_kernel<<<rg, 256, 0, st>>>(h->d_part, ksplit, stride, ld, coef, h->nmodes, nframes);
+            zmf_reduce_kernel<<<rg, 256, 0, st>>>(h->d_part, ksplit, stride, ld, coef, h->nmodes, nframes, h->d_off);
             if (cudaGetLastError() != cudaSuccess) return FMPC_ERR_CUDA;
             h->launches += 1;
         }
@@ -523,7 +549,7 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
     // generic path (odd frame sizes, > 72 modes): scalar FMA kernel
     constexpr int MC = 7, FT = 4, NT = 256;
     const int grid = (nframes + FT - 1) / FT;
-    zmf_fit_kernel<MC, FT, NT><<<grid, NT, 0, st>>>(h->d_W, h->d_mask, frames, coef, h->npix, h->nmodes, nframes);
+    zmf_fit_kernel<MC, FT, NT><<<grid, NT, 0, st>>>(h->d_W, h->d_mask, frames, coef, h->npix, h->nmodes, nframes, h->d_off);
     if (cudaGetLastError() != cudaSuccess) return FMPC_ERR_CUDA;
     h->launches += 1;
     return FMPC_OK;
@@ -547,5 +573,73 @@ int zmf_fit(zmf_handle *h, int nframes, const double *frames, double *coef, doub
     if (telapsed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); *telapsed = ms * 1e-3; }
     return FMPC_OK;
 }
+
+// =============================================================================================
+// Estimator step of the closed loop (README.md:478):  x_hat = lsqminnorm(A_s'A_s, A_s'(y - b_s)).
+// A_s'A_s is a fixed nmodes x nmodes SPD matrix (cond(A_s) = 9.3 for the reference's model_approx.mat), so
+// x_hat = W y - W b_s with W = inv(A_s'A_s) A_s' built once in extended precision on the host; the device part
+// is the same streaming GEMM as zernmodfit (all pixels inside the "pupil", no 16-byte row alignment assumed).
+// =============================================================================================
+int est_create(est_handle **out, int npix, int nmodes, const double *A_s, const double *b_s, int max_batch, int device)
+{
+    if (!out) return FMPC_ERR_NULL;
+    *out = nullptr;
+    if (!A_s) return FMPC_ERR_NULL;
+    if (npix < 1 || nmodes < 1 || nmodes > npix || npix > (1 << 26) || max_batch < 1) return FMPC_ERR_DIM;
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return FMPC_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return FMPC_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FMPC_ERR_CUDA;
+    zmf_handle *h = new (std::nothrow) zmf_handle();
+    if (!h) return FMPC_ERR_CUDA;
+    h->device = device; h->nL = 0; h->N = -1; h->npix = npix; h->npix_in = npix; h->nmodes = nmodes;
+    h->mask.assign(npix, 1);
+    const int P = npix, M = nmodes;
+    h->Z.assign(A_s, A_s + (size_t)P * M);                 // column-major npix x nmodes, like the Zernike basis
+    std::vector<long double> G((size_t)M * M, 0.0L);
+    for (int a = 0; a < M; ++a)
+        for (int b = a; b < M; ++b) {
+            long double sacc = 0.0L;
+            const double *za = &h->Z[(size_t)a * P], *zb = &h->Z[(size_t)b * P];
+            for (int p = 0; p < P; ++p) sacc += (long double)za[p] * zb[p];
+            G[(size_t)a * M + b] = G[(size_t)b * M + a] = sacc;
+        }
+    for (int j = 0; j < M; ++j) {
+        const long double g0 = G[(size_t)j * M + j];
+        long double d = g0;
+        for (int k = 0; k < j; ++k) d -= G[(size_t)j * M + k] * G[(size_t)j * M + k];
+        // (numerically) rank-deficient A_s: lsqminnorm would switch to its minimum-norm branch, which is not covered
+        if (!(d > 1e-13L * g0)) { delete h; return FMPC_ERR_NOT_PD; }
+        d = sqrtl(d);
+        G[(size_t)j * M + j] = d;
+        for (int i = j + 1; i < M; ++i) {
+            long double sacc = G[(size_t)i * M + j];
+            for (int k = 0; k < j; ++k) sacc -= G[(size_t)i * M + k] * G[(size_t)j * M + k];
+            G[(size_t)i * M + j] = sacc / d;
+        }
+    }
+    std::vector<double> W((size_t)M * P, 0.0), off(M, 0.0);
+    std::vector<long double> col(M), offl(M, 0.0L);
+    for (int p = 0; p < P; ++p) {
+        for (int j = 0; j < M; ++j) col[j] = h->Z[(size_t)j * P + p];
+        for (int j = 0; j < M; ++j) { long double sacc = col[j]; for (int k = 0; k < j; ++k) sacc -= G[(size_t)j * M + k] * col[k]; col[j] = sacc / G[(size_t)j * M + j]; }
+        for (int j = M - 1; j >= 0; --j) { long double sacc = col[j]; for (int k = j + 1; k < M; ++k) sacc -= G[(size_t)k * M + j] * col[k]; col[j] = sacc / G[(size_t)j * M + j]; }
+        for (int j = 0; j < M; ++j) { W[(size_t)j * P + p] = (double)col[j]; if (b_s) offl[j] += col[j] * (long double)b_s[p]; }
+    }
+    bool ok = linfit_upload(h, W, prop.multiProcessorCount, max_batch);
+    if (ok && b_s) {
+        for (int j = 0; j < M; ++j) off[j] = (double)offl[j];
+        ok = cudaMalloc(&h->d_off, (size_t)M * 8) == cudaSuccess && cudaMemcpy(h->d_off, off.data(), (size_t)M * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) { zmf_destroy(h); return FMPC_ERR_CUDA; }
+    *out = h;
+    return FMPC_OK;
+}
+
+void est_destroy(est_handle *h) { zmf_destroy(h); }
+int est_apply(est_handle *h, int nb, const double *y, double *x_hat, double *telapsed) { return zmf_fit(h, nb, y, x_hat, telapsed); }
+int est_apply_d(est_handle *h, int nb, const double *y, double *x_hat, void *stream) { return zmf_fit_d(h, nb, y, x_hat, stream); }
+long long est_launch_count(const est_handle *h) { return zmf_launch_count(h); }
 
 } // extern "C"
