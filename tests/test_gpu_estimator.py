@@ -60,3 +60,44 @@ def test_estimator_other_shapes_and_errors(pk):
     assert e.value.code == -13
     with pytest.raises(pk.FmpcError):
         pk.Estimator(rs.randn(3, 5), None)                             # more modes than pixels
+
+
+def test_c1_closed_loop_estimator_then_var1_solve(pk):
+    """BASELINE.json configs[0] in miniature: the reference's closed-loop step (README.md:444-570) with the estimator
+    of model_approx.mat in front of the VAR(1) fastMPC solve exactly as Fast_MPC/VAR_1 assembles it (ramp rows,
+    literal C), n = 27, m = 144, T = 10 -- GPU estimator + GPU solve against the lsqminnorm / dense oracles."""
+    from mpc_sensorlessao_b200 import synth
+    from oracle import fastmpc_dense as fd
+    g = np.load(GOLD)
+    A_s, b_s = g["A_s"][:, 1:], g["b_s"]
+    p = synth.make_problem(6, 10, var_order=1, drop_piston=True, u_bound=28.0)
+    K = 2
+    a = synth.aberrations(p, 1, K, seed=11, amp=0.3)[0]
+    rs = np.random.RandomState(12)
+    noise = 1e-3 * rs.randn(K, A_s.shape[0])
+    nu0 = rs.rand(K, p.T * p.n)
+    est = pk.Estimator(A_s, b_s, max_batch=1)
+    hb = pk.FastMPCBatch(p.A1, None, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, du_min=p.du_min,
+                         du_max=p.du_max, ramp_rows=True, var1_literal_bug=True, max_batch=1)
+    u_prev_g = np.zeros(p.m); u_prev_o = np.zeros(p.m)
+    zg = zo = None
+    for k in range(K):
+        # measurement of the residual aberration through the first-order PSF model, y = b_s + A_s x + noise
+        yg = b_s + A_s @ (a[k] + p.B @ u_prev_g) + noise[k]
+        yo = b_s + A_s @ (a[k] + p.B @ u_prev_o) + noise[k]
+        x0g = est.estimate(yg)[0][0]
+        x0o = er.estimate(A_s, b_s, yo[None])[0]
+        assert relerr(x0g, x0o) < 1e-9
+        X0 = U0 = None
+        if zg is not None:
+            Zs = np.vstack([zg.reshape(p.T, -1)[1:], zg.reshape(p.T, -1)[-1:]])
+            U0, X0 = Zs[None, :, :p.m], Zs[None, :, p.m:]
+            zo = np.vstack([zo.reshape(p.T, -1)[1:], zo.reshape(p.T, -1)[-1:]]).reshape(-1)
+        out = hb.step(x0g, None, None, None, X0, U0, nu0[k], u_prev=u_prev_g, kappa=0.01, niters=3)
+        zg = np.hstack([out["U"][0], out["X"][0]]).reshape(-1)
+        o = fd.Fast_MPC2_VAR1(p.Q, p.R, None, p.Qf, None, None, None, p.x_min, p.x_max, p.u_min, p.u_max, p.du_min, p.du_max,
+                              p.T, x0o, u_prev_o, p.A1, p.B, np.zeros(p.T * p.n), None, zo)
+        zo = o.mpc_fixed_log_newton(3, 0.01, nu0=nu0[k])
+        assert relerr(zg[:p.m], zo[:p.m]) < 1e-9, k
+        u_prev_g, u_prev_o = zg[:p.m].copy(), zo[:p.m].copy()
+    est.close(); hb.close()
