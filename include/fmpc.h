@@ -223,6 +223,10 @@ int zmf_npix_in(const zmf_handle *h);
  * (may be NaN, zernmodfit.m:30).  coef: nmodes x nf (column j = ad(:,1) of frame j). HOST buffers. */
 int zmf_fit(zmf_handle *h, int nframes, const double *frames, double *coef, double *telapsed);
 int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, void *stream);
+/* Synthesis, the step after the path (README.md:592-598  phase_cor = sum_j ad_cor(j) * Z_j):
+ * frames(:,:,f) = sum_j coef(j,f) Z_j inside the pupil, 0 outside.  coef: nmodes x nf, frames: nL x nL x nf (column-major). */
+int zmf_synth(zmf_handle *h, int nframes, const double *coef, double *frames, double *telapsed);   /* HOST buffers */
+int zmf_synth_d(zmf_handle *h, int nframes, const double *coef, double *frames, void *stream);     /* DEVICE buffers */
 /* Copies the host-side basis (npix_in x nmodes, col-major) / mask (nL*nL bytes, col-major) out, for tests. */
 int zmf_get_basis(const zmf_handle *h, double *Z);
 int zmf_get_mask(const zmf_handle *h, unsigned char *mask);

@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "fmpc_default_params", "fmpc_device_count", "fmpc_create", "fmpc_destroy", "fmpc_step", "fmpc_step_d",
     "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
-    "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d",
+    "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
     "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count",
 ]
@@ -113,6 +113,8 @@ def load_library():
     L.zmf_npix_in.argtypes = [vp]
     L.zmf_fit.argtypes = [vp, C.c_int, vp, vp, vp]
     L.zmf_fit_d.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.zmf_synth.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.zmf_synth_d.argtypes = [vp, C.c_int, vp, vp, vp]
     L.zmf_get_basis.argtypes = [vp, vp]
     L.zmf_get_mask.argtypes = [vp, vp]
     _lib = L

@@ -61,6 +61,11 @@ struct zmf_handle {
     double *d_Wf = nullptr;                // [group][ntile][lane][2] fragment-ordered W
     unsigned *d_ginfo = nullptr;           // per group: (first pixel / 8) | (pixel mask << 24)
     int ngroups = 0, ntiles = 0;
+    double *d_Zdev = nullptr;              // synthesis, generic kernel: Z (npix_in x nmodes, column-major) on the device
+    int *d_pin = nullptr;                  // synthesis, generic kernel: index of every frame pixel among the in-pupil samples (-1 outside)
+    double *d_Zf = nullptr;                // synthesis: [group of 8 pixels][k-step][lane] fragment-ordered Z' (zeros outside the pupil)
+    unsigned char *d_gmask = nullptr;      // synthesis: pupil mask byte of every 8-pixel group
+    int syn_ks = 0;                        // k-steps (4 modes each) of the synthesis kernel instantiation: 7 or 18
     double *d_off = nullptr;               // nmodes: constant subtracted from every output column (estimator: W b_s), or NULL
     double *d_part = nullptr;              // split-K partial sums [ksplit][nframes][8 ntiles]
     size_t part_doubles = 0;
@@ -331,6 +336,133 @@ cudaError_t zmf_launch_nt(const zmf_handle *h, int mt, int nframes, const double
 
 } // namespace
 
+
+// ---------------------------------------------------------------------------------------------
+// Synthesis (the step after the path, README.md:592-598:  phase_cor = sum_j ad_cor(j) Z_j):
+//   frames[f][p] = sum_j coef[f][j] Z[p][j]   inside the pupil, 0 outside.
+// HBM-write bound (8 nL^2 bytes per frame out, 8 nmodes in) and, at 2 nmodes flop per 8 bytes, again next to the FP64
+// ridge: M = 8 frames, N = 8 pixels, K = nmodes on the FP64 tensor pipe.  The coefficient fragments of a warp's frame
+// tiles stay in registers; Z' comes pre-permuted in fragment order through the same bulk-copy stages as W in the fit
+// kernel; every lane stores 16 bytes, 4 lanes one 64-byte run of a frame (streaming stores).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+template <int KS, int MT, int NW>
+__global__ void __launch_bounds__(NW * 32) zmf_synth_dmma_kernel(const double *__restrict__ Zf, const unsigned char *__restrict__ gmask, int ngroups,
+                                                                 int groups_per_split, const double *__restrict__ coef,
+                                                                 double *__restrict__ frames, int npix, int nmodes, int nframes)
+{
+    constexpr int CH = (KS <= 9) ? 16 : 8, GD = KS * 32;
+    extern __shared__ __align__(128) double zbuf[];             // ZSTAGES x CH x GD
+    __shared__ __align__(8) unsigned long long bars[ZSTAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
+    const int g_begin = blockIdx.y * groups_per_split;
+    const int g_end = min(ngroups, g_begin + groups_per_split);
+    const int nch = (g_end - g_begin + CH - 1) / CH;
+    const int f0 = (blockIdx.x * NW + warp) * 8 * MT;
+    if (tid == 0) {
+        for (int s = 0; s < ZSTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int c) {
+        const int s = c % ZSTAGES, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
+        const unsigned bytes = (unsigned)ng * GD * 8u, bar = smem_u32(&bars[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(zbuf + (size_t)s * CH * GD)), "l"(Zf + (size_t)g0 * GD), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0) for (int c = 0; c < ZSTAGES && c < nch; ++c) issue(c);
+
+    // A fragments: coef[frame f0 + 8 mt + gq][mode 4 s + q], zero beyond nmodes / nframes
+    double a[MT][KS];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int f = f0 + 8 * mt + gq;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int j = 4 * s + q;
+            a[mt][s] = (f < nframes && j < nmodes) ? __ldg(coef + (size_t)f * nmodes + j) : 0.0;
+        }
+    }
+    double *orow[MT];
+    bool ok[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int f = f0 + 8 * mt + gq;
+        ok[mt] = f < nframes;
+        orow[mt] = frames + (size_t)min(f, nframes - 1) * npix + 2 * q;
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int s = c % ZSTAGES;
+        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ZSTAGES) & 1);
+        while (!mbar_try_wait(bar, parity)) { }
+        const double *zb = zbuf + (size_t)s * CH * GD + lane;
+        const int g0 = g_begin + c * CH;
+#pragma unroll 2
+        for (int gi = 0; gi < CH; ++gi) {
+            const int g = g0 + gi;
+            if (g < g_end) {
+                double acc[MT][2];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
+                if (__ldg(gmask + g)) {                  // groups wholly outside the pupil are plain zero stores
+                    const double *zg = zb + (size_t)gi * GD;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const double b = zg[32 * ks];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) zdmma(acc[mt], a[mt][ks], b);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    if (ok[mt]) __stcs(reinterpret_cast<double2 *>(orow[mt] + (size_t)g * 8), make_double2(acc[mt][0], acc[mt][1]));
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && c + ZSTAGES < nch) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + ZSTAGES);
+        }
+    }
+}
+
+// generic synthesis (frame length not a multiple of 8, or > 72 modes): one thread per pixel
+__global__ void zmf_synth_kernel(const double *__restrict__ Z, const unsigned char *__restrict__ mask, const int *__restrict__ pin,
+                                 const double *__restrict__ coef, double *__restrict__ frames, int npix, int npix_in, int nmodes, int nframes)
+{
+    const size_t tot = (size_t)nframes * npix;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t f = e / npix;
+        const int p = (int)(e - f * npix);
+        double s = 0.0;
+        if (mask[p]) {
+            const int pi = pin[p];
+            for (int j = 0; j < nmodes; ++j) s = fma(__ldg(coef + f * nmodes + j), __ldg(Z + (size_t)j * npix_in + pi), s);
+        }
+        frames[e] = s;
+    }
+}
+
+template <int KS, int MT>
+cudaError_t zmf_launch_synth(const zmf_handle *h, int nframes, const double *coef, double *frames, int ksplit, int gps, cudaStream_t st)
+{
+    constexpr int CH = (KS <= 9) ? 16 : 8, NW = 8;
+    const size_t smem = (size_t)ZSTAGES * CH * KS * 32 * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(zmf_synth_dmma_kernel<KS, MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((nframes + NW * 8 * MT - 1) / (NW * 8 * MT), ksplit);
+    zmf_synth_dmma_kernel<KS, MT, NW><<<grid, NW * 32, smem, st>>>(h->d_Zf, h->d_gmask, h->npix / 8, gps, coef, frames, h->npix, h->nmodes, nframes);
+    return cudaGetLastError();
+}
+
+} // namespace
+
 // Uploads the least-squares operator W (nmodes x npix, row j contiguous over pixels, exact zeros where mask == 0) and
 // builds the DMMA tables; allocates staging for max_frames.  Shared by zmf_create and est_create.
 static bool linfit_upload(zmf_handle *h, const std::vector<double> &W, int sm_count, int max_frames)
@@ -459,6 +591,10 @@ void zmf_destroy(zmf_handle *h)
     if (h->d_ginfo) cudaFree(h->d_ginfo);
     if (h->d_part) cudaFree(h->d_part);
     if (h->d_off) cudaFree(h->d_off);
+    if (h->d_Zf) cudaFree(h->d_Zf);
+    if (h->d_gmask) cudaFree(h->d_gmask);
+    if (h->d_Zdev) cudaFree(h->d_Zdev);
+    if (h->d_pin) cudaFree(h->d_pin);
     if (h->d_frames) cudaFree(h->d_frames);
     if (h->d_coef) cudaFree(h->d_coef);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -569,6 +705,95 @@ int zmf_fit(zmf_handle *h, int nframes, const double *frames, double *coef, doub
     if (rc) return rc;
     cudaEventRecord(h->ev1, st);
     if (cudaMemcpyAsync(coef, h->d_coef, (size_t)nframes * h->nmodes * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return FMPC_ERR_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return FMPC_ERR_CUDA;
+    if (telapsed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); *telapsed = ms * 1e-3; }
+    return FMPC_OK;
+}
+
+
+/* ---- synthesis: frames = Z coef inside the pupil, 0 outside (README.md:592-598) ---- */
+static int zmf_synth_prepare(zmf_handle *h)
+{
+    if (h->d_Zf || h->d_Zdev) return FMPC_OK;
+    const int P = h->npix_in, M = h->nmodes;
+    std::vector<int> pin(h->npix, -1);
+    { int k = 0; for (int p = 0; p < h->npix; ++p) if (h->mask[p]) pin[p] = k++; }
+    if (h->npix % 8 == 0 && M <= 72) {
+        const int KS = (M <= 28) ? 7 : 18, ng = h->npix / 8;
+        std::vector<double> Zf((size_t)ng * KS * 32, 0.0);
+        std::vector<unsigned char> gm(ng, 0);
+        for (int g = 0; g < ng; ++g)
+            for (int ks = 0; ks < KS; ++ks)
+                for (int ln = 0; ln < 32; ++ln) {
+                    const int px = 8 * g + (ln >> 2), j = 4 * ks + (ln & 3);
+                    if (h->mask[px]) { gm[g] = 1; if (j < M) Zf[((size_t)g * KS + ks) * 32 + ln] = h->Z[(size_t)j * P + pin[px]]; }
+                }
+        if (cudaMalloc(&h->d_Zf, Zf.size() * 8) != cudaSuccess || cudaMalloc(&h->d_gmask, gm.size() + 16) != cudaSuccess) return FMPC_ERR_CUDA;
+        if (cudaMemcpy(h->d_Zf, Zf.data(), Zf.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->d_gmask, gm.data(), gm.size(), cudaMemcpyHostToDevice) != cudaSuccess) return FMPC_ERR_CUDA;
+        h->syn_ks = KS;
+    } else {
+        if (cudaMalloc(&h->d_Zdev, h->Z.size() * 8) != cudaSuccess || cudaMalloc(&h->d_pin, (size_t)h->npix * 4) != cudaSuccess) return FMPC_ERR_CUDA;
+        if (cudaMemcpy(h->d_Zdev, h->Z.data(), h->Z.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->d_pin, pin.data(), (size_t)h->npix * 4, cudaMemcpyHostToDevice) != cudaSuccess) return FMPC_ERR_CUDA;
+    }
+    return FMPC_OK;
+}
+
+int zmf_synth_d(zmf_handle *h, int nframes, const double *coef, double *frames, void *stream)
+{
+    if (!h || !frames || !coef) return FMPC_ERR_NULL;
+    if (nframes <= 0) return nframes < 0 ? FMPC_ERR_DIM : FMPC_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) return FMPC_ERR_CUDA;
+    int rc = zmf_synth_prepare(h);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if (h->d_Zf && ((uintptr_t)frames & 15) == 0) {
+        const int mt = (nframes > 4096) ? 2 : 1;
+        const int fblocks = (nframes + 64 * mt - 1) / (64 * mt), ng = h->npix / 8;
+        int ksplit = (6 * h->sm_count + fblocks - 1) / fblocks;      // split over pixel groups: independent outputs, no reduction
+        if (ksplit > 32) ksplit = 32;
+        if (ksplit > (ng + 63) / 64) ksplit = (ng + 63) / 64;
+        if (ksplit < 1) ksplit = 1;
+        int gps = (ng + ksplit - 1) / ksplit;
+        gps = (gps + 15) & ~15;
+        ksplit = (ng + gps - 1) / gps;
+        cudaError_t e;
+        if (h->syn_ks == 7) e = (mt == 2) ? zmf_launch_synth<7, 2>(h, nframes, coef, frames, ksplit, gps, st) : zmf_launch_synth<7, 1>(h, nframes, coef, frames, ksplit, gps, st);
+        else e = (mt == 2) ? zmf_launch_synth<18, 2>(h, nframes, coef, frames, ksplit, gps, st) : zmf_launch_synth<18, 1>(h, nframes, coef, frames, ksplit, gps, st);
+        if (e != cudaSuccess) return FMPC_ERR_CUDA;
+    } else {
+        if (!h->d_Zdev) {       // DMMA tables exist but the output is not 16-byte aligned: build the generic tables too
+            std::vector<int> pin(h->npix, -1);
+            { int k = 0; for (int p = 0; p < h->npix; ++p) if (h->mask[p]) pin[p] = k++; }
+            if (cudaMalloc(&h->d_Zdev, h->Z.size() * 8) != cudaSuccess || cudaMalloc(&h->d_pin, (size_t)h->npix * 4) != cudaSuccess) return FMPC_ERR_CUDA;
+            if (cudaMemcpy(h->d_Zdev, h->Z.data(), h->Z.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMemcpy(h->d_pin, pin.data(), (size_t)h->npix * 4, cudaMemcpyHostToDevice) != cudaSuccess) return FMPC_ERR_CUDA;
+        }
+        const size_t tot = (size_t)nframes * h->npix;
+        int grid = (int)((tot + 255) / 256);
+        if (grid > h->sm_count * 16) grid = h->sm_count * 16;
+        zmf_synth_kernel<<<grid, 256, 0, st>>>(h->d_Zdev, h->d_mask, h->d_pin, coef, frames, h->npix, h->npix_in, h->nmodes, nframes);
+        if (cudaGetLastError() != cudaSuccess) return FMPC_ERR_CUDA;
+    }
+    h->launches += 1;
+    return FMPC_OK;
+}
+
+int zmf_synth(zmf_handle *h, int nframes, const double *coef, double *frames, double *telapsed)
+{
+    if (!h || !frames || !coef) return FMPC_ERR_NULL;
+    if (telapsed) *telapsed = 0.0;
+    if (nframes <= 0) return nframes < 0 ? FMPC_ERR_DIM : FMPC_OK;
+    if ((size_t)nframes > h->cap_frames) return FMPC_ERR_BATCH;
+    if (cudaSetDevice(h->device) != cudaSuccess) return FMPC_ERR_CUDA;
+    cudaStream_t st = h->stream;
+    if (cudaMemcpyAsync(h->d_coef, coef, (size_t)nframes * h->nmodes * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return FMPC_ERR_CUDA;
+    cudaEventRecord(h->ev0, st);
+    int rc = zmf_synth_d(h, nframes, h->d_coef, h->d_frames, st);
+    if (rc) return rc;
+    cudaEventRecord(h->ev1, st);
+    if (cudaMemcpyAsync(frames, h->d_frames, (size_t)nframes * h->npix * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return FMPC_ERR_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return FMPC_ERR_CUDA;
     if (telapsed) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); *telapsed = ms * 1e-3; }
     return FMPC_OK;

@@ -75,6 +75,21 @@ class ZernikeFitter:
         return coef, tel.value
 
 
+    def synth(self, coef: np.ndarray):
+        """coef: (nf, nmodes) -> (frames (nf, nL, nL) with frames[j][row, col] = sum_k coef[j, k] Z_k(row, col) inside the
+        pupil and 0 outside (README.md:592-598), telapsed seconds)."""
+        coef = np.ascontiguousarray(np.asarray(coef, dtype=np.float64))
+        if coef.ndim == 1:
+            coef = coef.reshape(1, -1)
+        if coef.shape[1] != self.nmodes:
+            raise ValueError("coef must be (nf, nmodes)")
+        nf = coef.shape[0]
+        out = np.empty((nf, self.nL, self.nL))
+        tel = C.c_double(0.0)
+        check(self._L.zmf_synth(self._h, nf, _ptr(coef), _ptr(out), C.cast(C.byref(tel), C.c_void_p)))
+        return np.ascontiguousarray(np.transpose(out, (0, 2, 1))), tel.value
+
+
 _fitters = {}
 
 

@@ -58,6 +58,23 @@ def bench_zmf():
                           "roofline": {"bound": "hbm", "achieved": byts / ms / 1e6, "peak": HBM, "unit": "GB/s", "frac": byts / ms / 1e6 / HBM,
                                        "bytes_per_frame": byts // nf},
                           "fp64_tflops": 2 * nm * zf.npix_in * nf / ms / 1e9}), flush=True)
+        # synthesis (README.md:592-598): frames = Z coef, HBM-write bound
+        ts = []
+        for it in range(8):
+            flush.fill_(it)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = L.zmf_synth_d(zf._h, nf, vp(coef), vp(frames), C.c_void_p(st.cuda_stream))
+            e1.record(st)
+            torch.cuda.synchronize()
+            assert rc == 0
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts[2:]))
+        print(json.dumps({"workload": f"Zernike synthesis N=6, {nf} frames 128x128", "kernel_ms": ms, "frames_per_s": nf / ms * 1e3,
+                          "roofline": {"bound": "hbm", "achieved": byts / ms / 1e6, "peak": HBM, "unit": "GB/s", "frac": byts / ms / 1e6 / HBM,
+                                       "bytes_per_frame": byts // nf},
+                          "fp64_tflops": 2 * nm * zf.npix_in * nf / ms / 1e9}), flush=True)
         zf.close()
 
 

@@ -87,3 +87,40 @@ def test_dmma_path_shapes(pk, nL, N, nf):
     if nf <= 70:
         assert relerr(coef, zr.fit_frames_literal(frames, N)) < TOL
     zf.close()
+
+
+@pytest.mark.parametrize("nL,N,nf", [(128, 6, 5), (128, 6, 300), (128, 10, 66), (64, 3, 4200), (50, 4, 9), (16, 12, 3)])
+def test_synthesis_matches_basis(pk, nL, N, nf):
+    """zmf_synth (README.md:592-598, phase_cor = sum_j ad_cor(j) Z_j): frames = Z coef inside the pupil, 0 outside; and
+    fit(synth(c)) == c (the two kernels are each other's pseudo-inverse on the pupil)."""
+    zf = pk.ZernikeFitter(nL, N, max_frames=nf)
+    r, th, is_in = zr.pupil_grid(nL)
+    n_, m_ = zr.mode_indices(N)
+    Z = zr.zernfun(n_, m_, r, th)
+    c = np.random.RandomState(nf).randn(nf, Z.shape[1])
+    frames, tel = zf.synth(c)
+    ref = np.zeros((nf, nL * nL))
+    ref[:, is_in.T.reshape(-1)] = c @ Z.T
+    ref = ref.reshape(nf, nL, nL).transpose(0, 2, 1)
+    assert relerr(frames, ref) < 1e-13 and tel > 0
+    assert (frames[:, ~is_in] == 0).all()
+    back, _ = zf.fit(frames)
+    assert relerr(back, c) < TOL
+    zf.close()
+
+
+def test_dm_influence_matrix_is_a_zernike_fit(pk):
+    """README.md:196-271: B = pinv(Z'Z) Z' I -- the influence matrix is zernmodfit applied to the 144 actuator
+    influence functions, i.e. one zmf_fit call with the influence functions as frames."""
+    from mpc_sensorlessao_b200 import synth
+    nL, N, m1 = 128, 6, 12
+    B_ref = synth.influence_matrix(N, m1, 0.1, nL, False)                # host construction used by the benchmark problems
+    x = np.arange(-(nL - 1), nL, 2) / (nL - 1)
+    X, Y = np.meshgrid(x, x)
+    ax = np.linspace(-1.0, 1.0, m1)
+    d = ax[1] - ax[0]
+    infl = np.array([np.exp(np.log(0.1) * ((X - ax[j]) ** 2 + (Y + ax[i]) ** 2) / d ** 2) for i in range(m1) for j in range(m1)])
+    zf = pk.ZernikeFitter(nL, N, max_frames=m1 * m1)
+    B, _ = zf.fit(infl)
+    zf.close()
+    assert B.T.shape == B_ref.shape and relerr(B.T, B_ref) < TOL
