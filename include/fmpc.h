@@ -193,7 +193,7 @@ long long fmpc_launch_count(const fmpc_handle *h);
  * requires a device sync, so call it outside timed regions. */
 long long fmpc_last_newton_iters(fmpc_handle *h);
 /* Which solve kernel the handle selected: 2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA-per-instance
- * DMMA kernel (experiments), 0 = generic kernel (any n), 3 = general-structure kernel (VAR_1 ramp rows, literal
+ * DMMA kernel (32 < n <= 72), 0 = generic kernel (n > 72), 3 = general-structure kernel (VAR_1 ramp rows, literal
  * VAR_1 columns, dense Q / Qf). */
 int fmpc_kernel_kind(const fmpc_handle *h);
 /* Phase cycle counters of the last solve launch, summed over warps (all zero unless the library was

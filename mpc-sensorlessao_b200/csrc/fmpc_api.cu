@@ -265,7 +265,7 @@ const char *fmpc_strerror(int code)
     case FMPC_ERR_B_SIZE: return "The equality control dynamics matrix size does not match";
     case FMPC_ERR_INIT_SIZE: return "Initialization size mismatch (T*(n+m))";
     case FMPC_ERR_NOT_PD: return "cost matrix is not positive definite";
-    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (non-diagonal R, or a literal VAR_1 C that MATLAB itself would reject; see DESIGN.md)";
+    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (non-diagonal R, n > 72, or a literal VAR_1 C that MATLAB itself would reject; see DESIGN.md)";
     case FMPC_ERR_BATCH: return "nbatch exceeds the handle's max_batch";
     case FMPC_ERR_CUDA: return "no usable sm_100 CUDA device or CUDA runtime error (there is no CPU fallback)";
     case FMPC_ERR_PARAM: return "invalid solver parameter";
@@ -379,7 +379,9 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
             if (rc2 == 0) { h->cfg.slots = h->cfg.grid; h->cfg.ws_stride = L.total; }
         }
         if (rc2 != 0) {
-            if (fmpc_solve_config(S, device, &h->cfg) != 0) ok = false;
+            const int rc1 = fmpc_solve_config(S, device, &h->cfg);
+            if (rc1 == -2) { fmpc_destroy(h); return FMPC_ERR_UNSUPPORTED; }     // state blocks too large for shared memory (n > 72)
+            if (rc1 != 0) ok = false;
             else { h->cfg.slots = h->cfg.grid; h->cfg.ws_stride = L.total; }
         }
     }

@@ -90,9 +90,9 @@ struct GenSys {
 // status words (mirror include/fmpc.h)
 enum { ST_OK = 0, ST_EARLY_EXIT = 1, ST_NOT_PD = 2, ST_LS_MAX = 3, ST_NONFINITE = 4 };
 
-// use_mma: 0 = generic CTA kernel (any n), 1 = CTA-per-instance DMMA kernel (n <= 32), 2 = warp-per-instance DMMA kernel (n <= 32),
+// use_mma: 0 = generic CTA kernel (any n), 1 = CTA-per-instance DMMA kernel (n <= 72; the default for 32 < n <= 72), 2 = warp-per-instance DMMA kernel (n <= 32),
 //          3 = general-structure kernel (ramp rows / literal VAR_1 columns / dense Q)
-struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; int slots; size_t ws_stride; };
+struct SolveLaunchCfg { int grid, block; size_t smem; int use_mma; int slots; size_t ws_stride; int np; /* block-size class of the CTA DMMA kernel */ };
 
 // kernels.cu
 int  fmpc_solve_config(const DevSys &S, int device, SolveLaunchCfg *cfg);        // 0 ok
@@ -102,7 +102,7 @@ void fmpc_launch_state_update(const DevSys &S, int nbatch, const double *x, cons
 void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int a_stride, double *X, double *U,
                             double *x0, double *x0_pre, double *u_prev, int first, void *stream);
 
-// kernel_mma.cu : DMMA path (n <= 32)
+// kernel_mma.cu : CTA-per-instance DMMA path (n <= 72)
 int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable
 void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
 

@@ -1,4 +1,8 @@
-// fastMPC batched Newton solve -- DMMA path for n <= 32 (sm_100a, fp64).
+// fastMPC batched Newton solve -- CTA-per-instance DMMA path (sm_100a, fp64): n <= 72.
+//   n <= 32 : 128 threads, 5 CTAs per SM (kept for A/B experiments: the warp-per-instance kernel is the default there)
+//   32 < n <= 72 : 256 threads, 1 CTA per SM, five 72 x 68 operand blocks in shared memory (196 KB) -- the kernel for the
+//                  66-mode / horizon-30 configuration (BASELINE.json configs[4]); the diagonal block is factored and
+//                  inverted by the whole CTA (cta_potrf_inverse) instead of one warp with a row per lane.
 //
 // Same algorithm and per-instance control flow as the generic kernel in fmpc_kernels.cu (one persistent
 // CTA per MPC instance; inf_newton_solver.m:10-41 on the block structure), but every dense contraction
@@ -24,10 +28,13 @@ using namespace fmpc_dev;
 
 namespace {
 
-constexpr int NTHREADS = 128;
-constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXTT = 3;             // horizon (column) tiles accumulated together by one warp
-constexpr int CTAS_PER_SM = 5;
+template <int NP> struct KCfg {
+    static constexpr int NTH = (NP > 32) ? 256 : 128;       // threads per CTA
+    static constexpr int MINB = (NP > 32) ? 1 : 5;          // resident CTAs per SM the register budget is set for
+    static constexpr int KSMAX = (NP + 3) / 4;              // k-steps of a block product
+    static constexpr int RMAX = (NP > 32) ? 2 : 1;          // rows per 4-lane group in the GEMV phases
+};
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b)
 {
@@ -37,7 +44,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, con
 
 struct Geom {
     int n, KP, ld, RP, nt, ks, lds, ldu, mp, ldp, TP, ntt;
-    __host__ __device__ static int kp_of(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 28 ? 28 : 32)); }
+    __host__ __device__ static int kp_of(int n) { return n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 28 ? 28 : (n <= 32 ? 32 : ((n + 7) & ~7)))); }   // n > 32: whole 8-column tiles (cta_potrf_inverse)
     __host__ __device__ static Geom make(int n, int m, int T)
     {
         Geom g;
@@ -47,7 +54,7 @@ struct Geom {
         g.RP = (g.KP + 7) & ~7;
         g.nt = g.RP / 8;
         g.ks = g.KP / 4;
-        g.lds = g.KP + 1;                                 // S scratch (odd: row-per-lane loads are conflict-free)
+        g.lds = (n <= 32) ? g.KP + 1 : g.ld;              // S scratch (n <= 32: odd, row-per-lane loads are conflict-free)
         g.ldu = g.KP + 2;                                 // U scratch (16 B aligned rows, conflict-free 128-bit row stores)
         g.mp = (m + 3) & ~3;
         g.ldp = (g.mp % 8 == 4) ? g.mp : g.mp + 4;
@@ -63,7 +70,8 @@ struct Geom {
         if (b > a) a = b;
         return (a + 1) & ~(size_t)1;
     }
-    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + 32 * 3 + 64 + 32 + 36; }
+    __host__ __device__ int vlen() const { return RP < 32 ? 32 : RP; }
+    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * 8 : 0); }
 };
 
 // C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory
@@ -187,6 +195,139 @@ __device__ __forceinline__ int warp_potrf_inverse(const double *bS, double *bU, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Whole CTA (n > 32): Cholesky of the n x n block in bS (lower triangle, leading dimension ld) and explicit inverse of
+// the factor, blocked by the 8 x 8 DMMA tile:
+//   for every block column kb:  warp 0 factors the diagonal tile (row per lane, shared memory) and inverts it;
+//                               panel rows  P = S[., kb] inv(L_kk)'  one thread per row;
+//                               trailing tiles  S[I,J] -= P_I P_J'  as DMMAs, one tile per warp task;
+//   inv(L) by block rows:       X[i,k] = -inv(L_ii) sum_{j=k}^{i-1} L[i,j] X[j,k]   (DMMAs; one (i,k) tile per warp),
+//                               X[k,k] = inv(L_kk) from the factorisation.
+// Rows / columns >= n of the last tile behave as identity.  bT is a scratch block (receives X); on exit
+// bS <- inv(L) zero padded to RP x ld and gLinv <- n x n row-major.  tmp: 64 doubles per warp + 64.
+// All threads must call it; returns 0 or failing column + 1 (the same value in every thread).
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, int RP, double *gLinv, int n, int tid, int nth,
+                                              double *tmp, int *s_info)
+{
+    const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5, gq = lane >> 2, q = lane & 3;
+    const int nt = RP / 8;
+    double *tLi = tmp;                                  // 8 x 8 inverse of the current diagonal tile
+    double *wtmp = tmp + 64 + 64 * wid;                 // per-warp 8 x 8 scratch
+    if (tid == 0) *s_info = 0;
+    for (int kb = 0; kb < nt; ++kb) {
+        __syncthreads();
+        if (wid == 0) {
+            // ---- diagonal tile in registers: lane r (< 8) owns row r, columns travel by shuffles ----
+            constexpr unsigned FULLM = 0xffffffffu;
+            const double *D = bS + (size_t)(8 * kb) * ld + 8 * kb;
+            const int r = lane & 7;
+            const bool rpad = (8 * kb + r >= n);
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = rpad ? ((c == r) ? 1.0 : 0.0) : ((c <= r) ? D[r * ld + c] : 0.0);
+            int info = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double d = __shfl_sync(FULLM, a[k], k);
+                if ((!(d > 0.0) || !(d < 1.0e300)) && !info) info = 8 * kb + k + 1;       // uniform: same d in every lane
+                const double l = a[k] * rsqrt(d);                                          // L(r,k) for r >= k (lane k: sqrt(d))
+                a[k] = l;
+#pragma unroll
+                for (int c = k + 1; c < 8; ++c) {
+                    const double lc = __shfl_sync(FULLM, l, c);
+                    if (r >= c) a[c] = fma(-l, lc, a[c]);
+                }
+            }
+            if (info) { if (lane == 0) *s_info = info; }
+            else {
+                // inverse of the 8 x 8 lower factor: lane j (< 8) builds column j, rows of L arrive by shuffles
+                double dg = a[0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) if (r == c) dg = a[c];
+                const double dinv = 1.0 / dg;
+                const int j = r;
+                double x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < i) sacc = fma(__shfl_sync(FULLM, a[k], i), x[k], sacc);
+                    const double di = __shfl_sync(FULLM, dinv, i);
+                    x[i] = (i < j) ? 0.0 : ((i == j) ? di : -sacc * di);
+                }
+                if (lane < 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { tLi[i * 8 + j] = x[i]; bT[(size_t)(8 * kb + i) * ld + 8 * kb + j] = x[i]; }
+                }
+            }
+        }
+        __syncthreads();
+        if (*s_info) return *s_info;
+        // ---- panel: rows below the diagonal tile ----
+        for (int r = 8 * (kb + 1) + tid; r < RP; r += nth) {
+            double *row = bS + (size_t)r * ld + 8 * kb;
+            double x[8], y[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = row[k];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (k <= c) sacc = fma(x[k], tLi[c * 8 + k], sacc);
+                y[c] = sacc;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) row[k] = y[k];
+        }
+        __syncthreads();
+        // ---- trailing update: tiles (I, J), kb < J <= I ----
+        const int R = nt - kb - 1, ntask = R * (R + 1) / 2;
+        for (int task = wid; task < ntask; task += nw) {
+            int it = 0;
+            while (task >= (it + 1) * (it + 2) / 2) ++it;
+            const int jt = task - it * (it + 1) / 2;
+            const int I = kb + 1 + it, J = kb + 1 + jt;
+            double p0 = 0.0, p1 = 0.0;
+            tile_nt(p0, p1, bS + (size_t)(8 * I + gq) * ld + 8 * kb + q, bS + (size_t)(8 * J + gq) * ld + 8 * kb + q, 2);
+            double *o = bS + (size_t)(8 * I + gq) * ld + 8 * J + 2 * q;
+            o[0] -= p0; o[1] -= p1;
+        }
+    }
+    __syncthreads();
+    // ---- inv(L) by block rows ----
+    for (int i = 1; i < nt; ++i) {
+        for (int k = wid; k < i; k += nw) {
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            for (int j = k; j < i; ++j) {
+                const double *Ap = bS + (size_t)(8 * i + gq) * ld + 8 * j + q;
+                const double *Bp = bT + (size_t)(8 * j + q) * ld + 8 * k + gq;
+                dmma(c0, c1, Ap[0], Bp[0]);
+                dmma(e0, e1, Ap[4], Bp[(size_t)4 * ld]);
+            }
+            __syncwarp();
+            wtmp[gq * 8 + 2 * q] = c0 + e0;
+            wtmp[gq * 8 + 2 * q + 1] = c1 + e1;
+            __syncwarp();
+            double x0 = 0.0, x1 = 0.0;
+            const double *Lp = bT + (size_t)(8 * i + gq) * ld + 8 * i + q;
+            dmma(x0, x1, Lp[0], wtmp[q * 8 + gq]);
+            dmma(x0, x1, Lp[4], wtmp[(4 + q) * 8 + gq]);
+            double *o = bT + (size_t)(8 * i + gq) * ld + 8 * k + 2 * q;
+            o[0] = -x0; o[1] = -x1;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < RP * ld; e += nth) {
+        const int i = e / ld, j = e - i * ld;
+        const double v = (i < n && j <= i) ? bT[e] : 0.0;
+        bS[e] = v;
+        if (i < n && j < n) gLinv[(size_t)i * n + j] = v;
+    }
+    return 0;
+}
+
 // Everything a phase needs; lives in registers / constant bank.
 struct KC {
     const DevSys &S;
@@ -194,6 +335,7 @@ struct KC {
     int tid, lane, wid, gq, q;
     int ld, nt, ks, mp, ldp, TP, ntt;
     double *Us, *Xs, *red;
+    int nth, nw;                        // threads / warps per CTA
 };
 
 // ---- out = sgn * (C v - sub)  for v staged as  Us [TP][ldp] (u-like rows t)  and  Xs [(TP+2)][ld]
@@ -203,7 +345,7 @@ __device__ __noinline__ void mma_apply_C(const KC &k, const double *sub, double 
 {
     const DevSys &S = k.S;
     const int n = k.n, m = k.m, T = k.T;
-    for (int mt = k.wid; mt < k.nt; mt += NWARPS) {
+    for (int mt = k.wid; mt < k.nt; mt += k.nw) {
         const int row = 8 * mt + k.gq;
         const bool rok = row < n;
         for (int tt0 = 0; tt0 < k.ntt; tt0 += MAXTT) {
@@ -234,7 +376,7 @@ __device__ __noinline__ void mma_apply_C(const KC &k, const double *sub, double 
         }
     }
     if (k.has_xf)
-        for (int r = k.tid; r < n; r += NTHREADS) {
+        for (int r = k.tid; r < n; r += k.nth) {
             const double v = k.Xs[(size_t)(T - 1 + 2) * k.ld + r] - sub[(size_t)T * n + r];
             out[(size_t)T * n + r] = negate ? -v : v;
         }
@@ -250,7 +392,7 @@ __device__ __noinline__ void mma_apply_Ct(const KC &k, const double *vglob, doub
     const DevSys &S = k.S;
     const int n = k.n, m = k.m, T = k.T;
     const int mtu = (m + 7) / 8;
-    for (int task = k.wid; task < mtu + k.nt; task += NWARPS) {
+    for (int task = k.wid; task < mtu + k.nt; task += k.nw) {
         const bool upart = task < mtu;
         const int mt = upart ? task : task - mtu;
         const int row = 8 * mt + k.gq;
@@ -300,7 +442,7 @@ __device__ __noinline__ void mma_apply_Ct(const KC &k, const double *vglob, doub
 __device__ __forceinline__ void stage_rows(const KC &k, const double *src, int nrows, int shift)
 {
     const int tot = (k.TP + 2) * k.ld;
-    for (int e = k.tid; e < tot; e += NTHREADS) {
+    for (int e = k.tid; e < tot; e += k.nth) {
         const int rr = e / k.ld, c = e - rr * k.ld, sr = rr - shift;
         k.Xs[e] = (sr >= 0 && sr < nrows && c < k.n) ? src[(size_t)sr * k.n + c] : 0.0;
     }
@@ -310,8 +452,9 @@ __device__ __forceinline__ void stage_rows(const KC &k, const double *src, int n
 
 // =============================================================================================
 template <int NP>
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(const DevSys S, const StepArgs A)
+__global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kernel_mma(const DevSys S, const StepArgs A)
 {
+    constexpr int NTHREADS = KCfg<NP>::NTH, NWARPS = NTHREADS / 32, KSMAX = KCfg<NP>::KSMAX, RMAX = KCfg<NP>::RMAX;
     extern __shared__ double smem[];
     const int n = S.n, m = S.m, T = S.T;
     const int NB = T + (A.has_xf ? 1 : 0);
@@ -324,13 +467,15 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
 
     double *ops = smem;                                     // 5 operand blocks | staging (Us + Xs)
     double *Us = ops, *Xs = ops + (size_t)TP * ldp;
-    double *sm_rhs = smem + G.ops_doubles();                // 32
-    double *sm_y1 = sm_rhs + 32, *sm_y2 = sm_y1 + 32;       // y_{i-1}, y_{i-2}
-    double *colbuf = sm_y2 + 32;                            // 64
-    double *rsv = colbuf + 64;                              // 32
-    double *red = rsv + 32;                                 // 36
-    __shared__ int s_inst, s_flag;
-    const KC kc{S, n, m, T, NB, A.has_xf, tid, lane, wid, gq, q, ld, nt, ks, mp, ldp, TP, G.ntt, Us, Xs, red};
+    const int VL = G.vlen();
+    double *sm_rhs = smem + G.ops_doubles();                // VL
+    double *sm_y1 = sm_rhs + VL, *sm_y2 = sm_y1 + VL;       // y_{i-1}, y_{i-2}
+    double *colbuf = sm_y2 + VL;                            // 64
+    double *rsv = colbuf + 64;                              // VL
+    double *red = rsv + VL;                                 // 36
+    __shared__ int s_inst, s_flag, s_info2;
+    double *ptmp = red + 36;                                // potrf scratch (n > 32): 64 + 64 per warp
+    const KC kc{S, n, m, T, NB, A.has_xf, tid, lane, wid, gq, q, ld, nt, ks, mp, ldp, TP, G.ntt, Us, Xs, red, NTHREADS, NWARPS};
 
     double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
     double *nu = ws + L.nu, *dnu = ws + L.dnu, *yv = ws + L.yv, *bv = ws + L.bv;
@@ -531,22 +676,25 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                     }
                 }
                 // rhs_i = yv_i - L1p y_{i-1} - L2pp y_{i-2}   (4 lanes per row)
-                {
-                    const int r = tid >> 2;
-                    if (r < RP) {
-                        double s = 0.0;
-                        if (up1) for (int k = q; k < KP; k += 4) s = fma(bL1p[r * ld + k], sm_y1[k], s);
-                        if (up2) for (int k = q; k < KP; k += 4) s = fma(bL2pp[r * ld + k], sm_y2[k], s);
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        s += __shfl_xor_sync(0xffffffffu, s, 2);
-                        if (q == 0) sm_rhs[r] = (r < n) ? yv[i * n + r] - s : 0.0;
-                    }
+                for (int r = tid >> 2; r < RP; r += NTHREADS / 4) {          // RP is a multiple of 8: uniform per warp
+                    double s = 0.0;
+                    if (up1) for (int k = q; k < KP; k += 4) s = fma(bL1p[r * ld + k], sm_y1[k], s);
+                    if (up2) for (int k = q; k < KP; k += 4) s = fma(bL2pp[r * ld + k], sm_y2[k], s);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (q == 0) sm_rhs[r] = (r < n) ? yv[i * n + r] - s : 0.0;
                 }
                 __syncthreads();
                 // -- phase 2: factor + invert the diagonal block (one warp, rotating over the SM sub-partitions) --
-                if (wid == (i & (NWARPS - 1))) {
-                    const int info = warp_potrf_inverse<NP>(bS, bL2pp, bLinv, ld, gLi + (size_t)i * nn, n, colbuf, rsv, lane);
-                    if (lane == 0) s_flag = info;
+                if constexpr (NP > 32) {
+                    const int info = cta_potrf_inverse(bS, bL2pp, ld, RP, gLi + (size_t)i * nn, n, tid, NTHREADS, ptmp, &s_info2);
+                    __syncthreads();
+                    if (tid == 0) s_flag = info;
+                } else {
+                    if (wid == (i & (NWARPS - 1))) {
+                        const int info = warp_potrf_inverse<(NP > 32 ? 32 : NP)>(bS, bL2pp, bLinv, ld, gLi + (size_t)i * nn, n, colbuf, rsv, lane);
+                        if (lane == 0) s_flag = info;
+                    }
                 }
                 __syncthreads();
                 if (s_flag) { fail = true; break; }
@@ -555,16 +703,16 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                 for (int rt = wid; rt < nt; rt += NWARPS) {
                     const int r = 8 * rt + gq;
                     if (has1) {
-                        double af[8];
+                        double af[KSMAX];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) af[k] = (k < ks) ? bM1[r * ld + 4 * k + q] : 0.0;
+                        for (int k = 0; k < KSMAX; ++k) af[k] = (k < ks) ? bM1[r * ld + 4 * k + q] : 0.0;
                         __syncwarp();
                         for (int ct = 0; ct < nt; ++ct) {
                             double c0 = 0.0, c1 = 0.0;
                             const int kmax = min(ks, 2 * (ct + 1));          // inv(L) is lower triangular
                             const double *Bp = bLinv + (8 * ct + gq) * ld + q;
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
+                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
                             const int cc = 8 * ct + 2 * q;
                             if (cc < KP) bM1[r * ld + cc] = c0;
                             if (cc + 1 < KP) bM1[r * ld + cc + 1] = c1;
@@ -576,9 +724,9 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                     }
                     if (has2) {
                         const int y2 = S.y2i[i];
-                        double af[8];
+                        double af[KSMAX];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < KSMAX; ++k) {
                             const int kk = 4 * k + q;
                             af[k] = (y2 >= 0 && r < n && kk < n) ? __ldg(S.ypool + (size_t)y2 * nn + r * n + kk) : 0.0;
                         }
@@ -587,7 +735,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                             const int kmax = min(ks, 2 * (ct + 1));
                             const double *Bp = bLinv + (8 * ct + gq) * ld + q;
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
+                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
                             const int cc = 8 * ct + 2 * q;
                             if (cc < KP) bM2[r * ld + cc] = c0;
                             if (cc + 1 < KP) bM2[r * ld + cc + 1] = c1;
@@ -606,16 +754,25 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                     }
                 }
                 {
-                    const int r = tid >> 2;
-                    double s = 0.0;
-                    if (r < RP) for (int k = q; k < KP; k += 4) s = fma(bLinv[r * ld + k], sm_rhs[k], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    double sv[RMAX];
+#pragma unroll
+                    for (int u = 0; u < RMAX; ++u) {
+                        const int r = (tid >> 2) + u * (NTHREADS / 4);
+                        double s = 0.0;
+                        if (r < RP) for (int k = q; k < KP; k += 4) s = fma(bLinv[r * ld + k], sm_rhs[k], s);
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        sv[u] = s;
+                    }
                     __syncthreads();                               // everyone is done with sm_y1 / sm_y2 / the *p blocks of this stage
-                    if (r < RP && q == 0) {
-                        if (r < n) yv[i * n + r] = s;
-                        sm_y2[r] = sm_y1[r];
-                        sm_y1[r] = (r < n) ? s : 0.0;
+#pragma unroll
+                    for (int u = 0; u < RMAX; ++u) {
+                        const int r = (tid >> 2) + u * (NTHREADS / 4);
+                        if (r < RP && q == 0) {
+                            if (r < n) yv[i * n + r] = sv[u];
+                            sm_y2[r] = sm_y1[r];
+                            sm_y1[r] = (r < n) ? sv[u] : 0.0;
+                        }
                     }
                 }
                 {   // rotate the rings: L1p <-> M1 ; L2pp (now L2_i) becomes L2p, old L2p becomes L2pp
@@ -629,8 +786,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
             // ---- backward solve  dnu_i = inv(L_i)' (y_i - L1_i' dnu_{i+1} - L2_i' dnu_{i+2})  (:32) ----
             for (int i = NB - 1; i >= 0; --i) {
                 const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && S.has_a2;
-                {   // v[k] : 4 threads per column k, rows split by q
-                    const int k = tid >> 2;
+                for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {   // v[k] : 4 threads per column k, rows split by q
                     double s = 0.0;
                     if (k < n) {
                         if (has1) for (int r = q; r < n; r += 4) s = fma(gL1[(size_t)i * nn + r * n + k], dnu[(i + 1) * n + r], s);
@@ -641,8 +797,7 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) fmpc_solve_kernel_mma(c
                     if (k < n && q == 0) sm_rhs[k] = yv[i * n + k] - s;
                 }
                 __syncthreads();
-                {
-                    const int k = tid >> 2;
+                for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {
                     double s = 0.0;
                     if (k < n) for (int r = k + q; r < n; r += 4) s = fma(gLi[(size_t)i * nn + r * n + k], sm_rhs[r], s);
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -732,23 +887,25 @@ static int config_np(const Geom &G, SolveLaunchCfg *cfg, int sms)
     const size_t smem = G.smem_doubles() * sizeof(double);
     if (cudaFuncSetAttribute(fmpc_solve_kernel_mma<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -4;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_mma<NP>, NTHREADS, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_mma<NP>, KCfg<NP>::NTH, smem) != cudaSuccess || per_sm < 1)
         return -5;
     if (const char *e = getenv("FMPC_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // experiments
     cfg->grid = sms * per_sm;
-    cfg->block = NTHREADS;
+    cfg->block = KCfg<NP>::NTH;
     cfg->smem = smem;
-    cfg->use_mma = NP;
+    cfg->use_mma = 1;
+    cfg->np = NP;
     return 0;
 }
 
 int fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg)
 {
-    if (S.n > 32) return -1;
+    if (S.n > 72) return -1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -2;
     const Geom G = Geom::make(S.n, S.m, S.T);
     if (G.smem_doubles() * sizeof(double) > (size_t)prop.sharedMemPerBlockOptin) return -3;
+    if (S.n > 32) return config_np<72>(G, cfg, prop.multiProcessorCount);
     switch (G.KP) {
     case 8: return config_np<8>(G, cfg, prop.multiProcessorCount);
     case 16: return config_np<16>(G, cfg, prop.multiProcessorCount);
@@ -762,7 +919,8 @@ void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunch
     int grid = cfg.grid < A.nbatch ? cfg.grid : A.nbatch;
     if (grid < 1) grid = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (cfg.use_mma) {
+    switch (cfg.np) {
+    case 72: fmpc_solve_kernel_mma<72><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
     case 8: fmpc_solve_kernel_mma<8><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
     case 16: fmpc_solve_kernel_mma<16><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;
     case 28: fmpc_solve_kernel_mma<28><<<grid, cfg.block, cfg.smem, st>>>(S, A); break;

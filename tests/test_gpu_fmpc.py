@@ -56,6 +56,11 @@ SMALL = [
     dict(seed=18, n=32, m=16, T=5, nb=2, umax=0.4, warm=True, xf=True),
     dict(seed=19, n=28, m=144, T=20, nb=40, umax=0.5, warm=True, xf=True),   # more instances than one CTA holds
     dict(seed=20, n=8, m=6, T=17, nb=9, umax=0.3, a2=False, xf=True, warm=True),
+    # 32 < n <= 72: the 256-thread CTA DMMA kernel (whole-CTA potrf + inverse)
+    dict(seed=21, n=72, m=10, T=4, nb=2, umax=0.4, warm=True, xf=True),
+    dict(seed=22, n=40, m=50, T=9, nb=3, umax=0.4, a2=False, warm=True),
+    dict(seed=23, n=65, m=30, T=3, nb=2, umax=0.5),
+    dict(seed=25, n=66, m=144, T=30, nb=150, umax=1.0, warm=True),   # C5 shape, more instances than SMs
 ]
 
 
@@ -79,12 +84,16 @@ def test_parity_vs_golden(pk, path):
 
 
 def test_kernel_selection(pk):
-    """n <= 32 runs on the warp-per-instance DMMA kernel, larger n on the generic kernel (never a CPU path)."""
-    for n, kind in ((6, 2), (28, 2), (32, 2), (33, 0)):
+    """n <= 32 runs on the warp-per-instance DMMA kernel, 32 < n <= 72 on the CTA-per-instance DMMA kernel (never a
+    CPU path); larger blocks do not fit the shared-memory block chain and are refused."""
+    for n, kind in ((6, 2), (28, 2), (32, 2), (33, 1), (66, 1), (72, 1)):
         c = small_problem(1, n, 4, 3, 1, 1.0)
         hb = make_handle(pk, c)
         assert hb.kernel_kind == kind
         hb.close()
+    with pytest.raises(pk.FmpcError) as e:
+        make_handle(pk, small_problem(1, 73, 4, 3, 1, 1.0))
+    assert e.value.code == -14
 
 
 def test_line_search_both_regimes(pk, fref):
