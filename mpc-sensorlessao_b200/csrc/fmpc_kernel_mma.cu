@@ -77,8 +77,16 @@ struct Geom {
 // C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory
 __device__ __forceinline__ void tile_nt(double &c0, double &c1, const double *A, const double *Bm, int ksteps)
 {
-#pragma unroll 4
-    for (int k = 0; k < ksteps; ++k) dmma(c0, c1, A[4 * k], Bm[4 * k]);
+    // two accumulation chains (even / odd k-steps): a dependent DMMA costs 28 cycles, an independent one 16
+    double e0 = 0.0, e1 = 0.0;
+    int k = 0;
+#pragma unroll 2
+    for (; k + 1 < ksteps; k += 2) {
+        dmma(c0, c1, A[4 * k], Bm[4 * k]);
+        dmma(e0, e1, A[4 * k + 4], Bm[4 * k + 4]);
+    }
+    if (k < ksteps) dmma(c0, c1, A[4 * k], Bm[4 * k]);
+    c0 += e0; c1 += e1;
 }
 
 // acc[tt] += A(row arow of a GLOBAL row-major matrix) * Bs(shared rows 8 tt + .., ldb)'
@@ -708,11 +716,12 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                         for (int k = 0; k < KSMAX; ++k) af[k] = (k < ks) ? bM1[r * ld + 4 * k + q] : 0.0;
                         __syncwarp();
                         for (int ct = 0; ct < nt; ++ct) {
-                            double c0 = 0.0, c1 = 0.0;
+                            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
                             const int kmax = min(ks, 2 * (ct + 1));          // inv(L) is lower triangular
                             const double *Bp = bLinv + (8 * ct + gq) * ld + q;
 #pragma unroll
-                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
+                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) { if (k & 1) dmma(e0, e1, af[k], Bp[4 * k]); else dmma(c0, c1, af[k], Bp[4 * k]); }
+                            c0 += e0; c1 += e1;
                             const int cc = 8 * ct + 2 * q;
                             if (cc < KP) bM1[r * ld + cc] = c0;
                             if (cc + 1 < KP) bM1[r * ld + cc + 1] = c1;
@@ -731,11 +740,12 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                             af[k] = (y2 >= 0 && r < n && kk < n) ? __ldg(S.ypool + (size_t)y2 * nn + r * n + kk) : 0.0;
                         }
                         for (int ct = 0; ct < nt; ++ct) {
-                            double c0 = 0.0, c1 = 0.0;
+                            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
                             const int kmax = min(ks, 2 * (ct + 1));
                             const double *Bp = bLinv + (8 * ct + gq) * ld + q;
 #pragma unroll
-                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) dmma(c0, c1, af[k], Bp[4 * k]);
+                            for (int k = 0; k < KSMAX; ++k) if (k < kmax) { if (k & 1) dmma(e0, e1, af[k], Bp[4 * k]); else dmma(c0, c1, af[k], Bp[4 * k]); }
+                            c0 += e0; c1 += e1;
                             const int cc = 8 * ct + 2 * q;
                             if (cc < KP) bM2[r * ld + cc] = c0;
                             if (cc + 1 < KP) bM2[r * ld + cc + 1] = c1;
