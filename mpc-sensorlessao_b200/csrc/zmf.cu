@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -139,7 +140,10 @@ template <int NT> struct ZChunk { static constexpr int CH = (NT <= 4) ? 16 : 8; 
 #define ZMF_PF 16
 #endif
 constexpr int ZPF = ZMF_PF;                                                           // L2 prefetch distance (groups), 0 = off
-constexpr int ZRING = 4;                                                             // frame-load ring depth (groups)
+#ifndef ZMF_RING1
+#define ZMF_RING1 8
+#endif
+template <int MT> struct ZRingDepth { static constexpr int V = (MT == 1) ? ZMF_RING1 : 4; };   // groups in flight per warp
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void zdmma(double (&c)[2], const double a, const double b)
@@ -161,6 +165,8 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
                                                                int npix, int nmodes, int nframes, const double *__restrict__ offv)
 {
     constexpr int CH = ZChunk<NT>::CH, GD = NT * 64;            // doubles of W per group
+    constexpr int ZRING = ZRingDepth<MT>::V;
+    static_assert(CH % ZRING == 0, "ring depth must divide the chunk");
     extern __shared__ __align__(128) double wbuf[];             // ZSTAGES x CH x GD
     __shared__ __align__(8) unsigned long long bars[ZSTAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
@@ -629,12 +635,16 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
     if (h->d_Wf) {
         // ---- DMMA path: frame-block size and split-K chosen so that the grid holds >= ~6 units per SM ----
         const bool vec = (h->npix % 8 == 0) && ((uintptr_t)frames & 15) == 0;      // 16-byte aligned rows of whole 8-pixel groups
-        int mt = (nframes > 4096) ? 2 : 1;
+        int mt = (nframes > 64) ? 2 : 1;                 // two frame tiles per warp share every W fragment
+        if (const char *e = getenv("ZMF_MT")) { const int v = atoi(e); if (v == 1 || v == 2) mt = v; }      // experiments
         if (!vec) mt = 1;
         const int fblocks = (nframes + 64 * mt - 1) / (64 * mt);
         constexpr int CHmin = 8;
-        int ksplit = (6 * h->sm_count + fblocks - 1) / fblocks;
+        // measured (scripts/zmf_sweep.sh, profiles/r01_zmf_sweep.log): ~14 work units per SM is the optimum at 2000 and at
+        // 32768 frames (deterministic split-K: partial sums + reduction kernel)
+        int ksplit = (14 * h->sm_count + fblocks - 1) / fblocks;
         if (ksplit > 16) ksplit = 16;
+        if (const char *e = getenv("ZMF_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 64) ksplit = v; }   // experiments
         const int maxsplit = (h->ngroups + 4 * CHmin - 1) / (4 * CHmin);      // keep >= 4 chunks per split
         if (ksplit > maxsplit) ksplit = maxsplit;
         if (ksplit < 1) ksplit = 1;

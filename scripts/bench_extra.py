@@ -34,10 +34,11 @@ def f_newton(n, m, T):
 
 
 def bench_zmf():
+    nL = int(os.environ.get("ZMF_NL", "128"))
     for nf in (2000, 32768):
-        zf = pk.ZernikeFitter(128, 6, max_frames=8)
+        zf = pk.ZernikeFitter(nL, 6, max_frames=8)
         nm = zf.nmodes
-        frames = torch.randn((nf, 128 * 128), dtype=torch.float64, device=dev)
+        frames = torch.randn((nf, nL * nL), dtype=torch.float64, device=dev)
         coef = torch.empty((nf, nm), dtype=torch.float64, device=dev)
         st = torch.cuda.Stream(dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -53,8 +54,8 @@ def bench_zmf():
             assert rc == 0
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts[2:]))
-        byts = nf * (8 * 128 * 128 + 8 * nm)
-        print(json.dumps({"workload": f"zernmodfit N=6, {nf} frames 128x128", "kernel_ms": ms, "frames_per_s": nf / ms * 1e3,
+        byts = nf * (8 * nL * nL + 8 * nm)
+        print(json.dumps({"workload": f"zernmodfit N=6, {nf} frames {nL}x{nL}", "kernel_ms": ms, "frames_per_s": nf / ms * 1e3,
                           "roofline": {"bound": "hbm", "achieved": byts / ms / 1e6, "peak": HBM, "unit": "GB/s", "frac": byts / ms / 1e6 / HBM,
                                        "bytes_per_frame": byts // nf},
                           "fp64_tflops": 2 * nm * zf.npix_in * nf / ms / 1e9}), flush=True)
@@ -71,7 +72,7 @@ def bench_zmf():
             assert rc == 0
             ts.append(e0.elapsed_time(e1))
         ms = float(np.median(ts[2:]))
-        print(json.dumps({"workload": f"Zernike synthesis N=6, {nf} frames 128x128", "kernel_ms": ms, "frames_per_s": nf / ms * 1e3,
+        print(json.dumps({"workload": f"Zernike synthesis N=6, {nf} frames {nL}x{nL}", "kernel_ms": ms, "frames_per_s": nf / ms * 1e3,
                           "roofline": {"bound": "hbm", "achieved": byts / ms / 1e6, "peak": HBM, "unit": "GB/s", "frac": byts / ms / 1e6 / HBM,
                                        "bytes_per_frame": byts // nf},
                           "fp64_tflops": 2 * nm * zf.npix_in * nf / ms / 1e9}), flush=True)
