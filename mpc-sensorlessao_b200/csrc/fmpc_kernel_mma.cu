@@ -30,7 +30,7 @@ namespace {
 
 constexpr int MAXTT = 3;             // horizon (column) tiles accumulated together by one warp
 template <int NP> struct KCfg {
-    static constexpr int NTH = (NP > 32) ? 256 : 128;       // threads per CTA
+    static constexpr int NTH = (NP > 32) ? 256 : 128;       // threads per CTA (9 warps for the 9 row tiles of a 72-row block measured no faster: registers)
     static constexpr int MINB = (NP > 32) ? 1 : 5;          // resident CTAs per SM the register budget is set for
     static constexpr int KSMAX = (NP + 3) / 4;              // k-steps of a block product
     static constexpr int RMAX = (NP > 32) ? 2 : 1;          // rows per 4-lane group in the GEMV phases
@@ -71,7 +71,7 @@ struct Geom {
         return (a + 1) & ~(size_t)1;
     }
     __host__ __device__ int vlen() const { return RP < 32 ? 32 : RP; }
-    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * 8 : 0); }
+    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * 9 : 0); }
 };
 
 // C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory

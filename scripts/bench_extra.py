@@ -119,7 +119,7 @@ def bench_c1(K=200):
                                        "steps_per_s": 1 / dt, "cores": os.cpu_count(), "sample": f"{nst} closed-loop steps"}}), flush=True)
 
 
-def bench_c5(nb=2048):
+def bench_c5(nb=int(os.environ.get("C5_NB", "2048"))):
     p = synth.make_problem(10, 30)
     wi = synth.warm_inputs(p, nb, seed=4)
     hb = pk.FastMPCBatch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, max_batch=nb)
