@@ -10,6 +10,8 @@
  *   x_next = fmpc_mex('state_update', h, x, x_pre, u, w)
  *   fmpc_mex('destroy', h)
  *   hz = fmpc_mex('zmf_create', nL, N, max_frames, device);  c = fmpc_mex('zmf_fit', hz, frames);  fmpc_mex('zmf_destroy', hz)
+ *   frames = fmpc_mex('zmf_synth', hz, coef)             coef: nmodes x nf  ->  nL x nL x nf  (README.md:592-598)
+ *   he = fmpc_mex('est_create', A_s, b_s, max_batch, device);  x_hat = fmpc_mex('est_apply', he, Y);  fmpc_mex('est_destroy', he)
  *
  * Build (on a machine with MATLAB):  mex -R2018a fmpc_mex.c -I../../include -L../lib -lfmpc_b200
  * Here it is only compile-checked against tests/stubs/mex.h (there is no MATLAB in the image).
@@ -150,8 +152,28 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         const int nf = mxGetNumberOfDimensions(prhs[2]) > 2 ? (int)d[2] : 1;
         plhs[0] = mxCreateDoubleMatrix(zmf_nmodes(h), nf, mxREAL);
         check(zmf_fit(h, nf, mxGetPr(prhs[2]), mxGetPr(plhs[0]), NULL));
+    } else if (!strcmp(cmd, "zmf_synth")) {
+        zmf_handle *h = (zmf_handle *)get_handle(prhs[1]);
+        const int nf = (int)mxGetN(prhs[2]);
+        const int nL = (int)mxGetScalar(prhs[3]);            /* frame size the handle was created with */
+        mwSize dims[3];
+        dims[0] = (mwSize)nL; dims[1] = (mwSize)nL; dims[2] = (mwSize)nf;
+        plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        check(zmf_synth(h, nf, mxGetPr(prhs[2]), mxGetPr(plhs[0]), NULL));
     } else if (!strcmp(cmd, "zmf_destroy")) {
         zmf_destroy((zmf_handle *)get_handle(prhs[1]));
+    } else if (!strcmp(cmd, "est_create")) {
+        est_handle *h = NULL;
+        check(est_create(&h, (int)mxGetM(prhs[1]), (int)mxGetN(prhs[1]), mxGetPr(prhs[1]), opt(prhs[2]),
+                         nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 1, nrhs > 4 ? (int)mxGetScalar(prhs[4]) : 0));
+        plhs[0] = put_handle(h);
+    } else if (!strcmp(cmd, "est_apply")) {
+        est_handle *h = (est_handle *)get_handle(prhs[1]);
+        const int nb = (int)mxGetN(prhs[2]);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)zmf_nmodes(h), (mwSize)nb, mxREAL);
+        check(est_apply(h, nb, mxGetPr(prhs[2]), mxGetPr(plhs[0]), NULL));
+    } else if (!strcmp(cmd, "est_destroy")) {
+        est_destroy((est_handle *)get_handle(prhs[1]));
     } else {
         mexErrMsgIdAndTxt("fmpc:usage", "unknown command '%s'", cmd);
     }

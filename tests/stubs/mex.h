@@ -22,6 +22,7 @@ int mxGetString(const mxArray *, char *, mwSize);
 mxArray *mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray *mxCreateDoubleScalar(double);
 mxArray *mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
+mxArray *mxCreateNumericArray(mwSize, const mwSize *, mxClassID, mxComplexity);
 void mxDestroyArray(mxArray *);
 void mexErrMsgIdAndTxt(const char *, const char *, ...);
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);
