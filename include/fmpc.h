@@ -246,6 +246,15 @@ int est_apply(est_handle *h, int nb, const double *y, double *x_hat, double *tel
 int est_apply_d(est_handle *h, int nb, const double *y, double *x_hat, void *stream);            /* DEVICE buffers */
 long long est_launch_count(const est_handle *h);
 
+/* ======================================================================================= */
+/* VAR(p) identification of the coefficient time series (README.md:116-130), batched:         */
+/*     AA(i-PN, n(j-1)+1:n j) = ad_acc(i-j,:), BB(i-PN,:) = ad_acc(i,:), i = PN+1..num_train   */
+/*     PARA = (AA'*AA)\AA'*BB;  A_j = PARA(n(j-1)+1:n j, :)'                                   */
+/*   ad   K x n x nseq   training series, column-major like ad_acc(1:num_train,:) (HOST)       */
+/*   A    n x n x order x nseq   A(:,:,j,s) = A_j of sequence s (HOST, output)                 */
+/*   info nseq | NULL    0, or failing column + 1 of chol(AA'AA) for that sequence             */
+int var_identify(int nseq, int K, int n, int order, const double *ad, double *A, int *info, int device, double *telapsed);
+
 #ifdef __cplusplus
 }
 #endif

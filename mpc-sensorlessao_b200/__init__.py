@@ -11,8 +11,8 @@ from ._lib import (FmpcError, FmpcParams, build_library, device_count, fp64_peak
                    strerror)
 from .fast_mpc2 import FastMPCBatch, Fast_MPC2, Fast_MPC2_VAR1, deinterleave, interleave
 from .zernike import ZernikeFitter, zernmodfit
-from .estimator import Estimator
+from .estimator import Estimator, identify_var
 
 __all__ = ["FmpcError", "FmpcParams", "build_library", "device_count", "fp64_peak", "lib_path", "load_library",
            "strerror", "FastMPCBatch", "Fast_MPC2", "Fast_MPC2_VAR1", "deinterleave", "interleave",
-           "ZernikeFitter", "zernmodfit", "Estimator"]
+           "ZernikeFitter", "zernmodfit", "Estimator", "identify_var"]

@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
     "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
-    "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count",
+    "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count", "var_identify",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
     L.fmpc_state_update.argtypes = [vp, C.c_int] + [vp] * 5
     L.fmpc_state_update_d.argtypes = [vp, C.c_int] + [vp] * 6
     L.fmpc_closed_loop.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6
+    L.var_identify.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     L.est_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]
     L.est_destroy.argtypes = [vp]
     L.est_destroy.restype = None

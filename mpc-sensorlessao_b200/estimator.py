@@ -59,3 +59,23 @@ class Estimator:
         tel = C.c_double(0.0)
         check(self._L.est_apply(self._h, nb, _ptr(Y), _ptr(out), C.cast(C.byref(tel), C.c_void_p)))
         return out, tel.value
+
+
+def identify_var(ad_acc, order: int = 2, device: int = 0):
+    """README.md:116-130 on the GPU.  ad_acc: (K, n) training series (rows = time, like ad_acc(1:num_train,:)) or a batch
+    (nseq, K, n).  Returns (A (order, n, n) or (nseq, order, n, n) with A[j-1] = A_j, telapsed seconds)."""
+    L = load_library()
+    a = np.asarray(ad_acc, dtype=np.float64)
+    single = a.ndim == 2
+    if single:
+        a = a[None]
+    nseq, K, n = a.shape
+    acm = np.ascontiguousarray(np.transpose(a, (0, 2, 1)))              # per sequence column-major K x n
+    out = np.empty((nseq, order, n, n))
+    info = np.zeros(nseq, dtype=np.int32)
+    tel = C.c_double(0.0)
+    check(L.var_identify(nseq, K, n, int(order), _ptr(acm), _ptr(out), _ptr(info), int(device), C.cast(C.byref(tel), C.c_void_p)))
+    if info.any():
+        raise np.linalg.LinAlgError(f"AA'*AA is not positive definite for sequences {np.nonzero(info)[0].tolist()}")
+    A = np.ascontiguousarray(np.transpose(out, (0, 1, 3, 2)))           # stored column-major n x n
+    return (A[0] if single else A), tel.value

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "fmpc.h")
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:fmpc|zmf|est)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:fmpc|zmf|est|var)_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_and_binding_list_agree(pk):
@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(pk):
     for sym in declared_symbols():
         assert hasattr(L, sym), f"{sym} declared in include/fmpc.h but not exported"
     out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T ((?:fmpc|zmf|est)_\w+)", out))
+    exported = set(re.findall(r" T ((?:fmpc|zmf|est|var)_\w+)", out))
     assert exported == set(declared_symbols()), "exported C-ABI symbols differ from the header"
 
 
