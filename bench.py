@@ -72,17 +72,55 @@ def host_threads():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): an in-process NVML thread
+    (nvidia_ml_py, one sample every ~5 ms -- the timed region is only ~60 ms long), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.sm, self.smax, self.reasons, self.stop_flag, self.thread, self.how = [], [], set(), False, None, None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve the NVML handle through the PCI bus id of the CUDA device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hh = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        h = hh
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))]
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.how = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -92,6 +130,12 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            if self.sm:
+                return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.smax)), "reasons": sorted(self.reasons),
+                        "samples": len(self.sm), "how": "nvml, 5 ms period, inside the timed region"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -112,7 +156,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm),
+                "how": "nvidia-smi -lms 50"}
 
 
 def run_reference(args, rank, world):
@@ -168,6 +213,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner to STDOUT when NCCL_DEBUG is VERSION/WARN: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
     L = load_library()
     nb = args.instances
