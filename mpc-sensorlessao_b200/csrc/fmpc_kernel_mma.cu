@@ -28,6 +28,10 @@ using namespace fmpc_dev;
 
 namespace {
 
+#ifndef FMPC_BW_SMEM
+#define FMPC_BW_SMEM 0      // backward substitution of the n > 32 kernel with the factor blocks prefetched by cp.async into shared
+                            // memory: parity-tested, but measured no faster on B200 at the C5 shape (51.5 k vs 49-53 k solves/s)
+#endif
 constexpr int MAXTT = 3;             // horizon (column) tiles accumulated together by one warp
 template <int NP> struct KCfg {
     static constexpr int NTH = (NP > 32) ? 256 : 128;       // threads per CTA (9 warps for the 9 row tiles of a 72-row block measured no faster: registers)
@@ -794,27 +798,74 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
             if (fail) { status = ST_NOT_PD; break; }
 
             // ---- backward solve  dnu_i = inv(L_i)' (y_i - L1_i' dnu_{i+1} - L2_i' dnu_{i+2})  (:32) ----
-            for (int i = NB - 1; i >= 0; --i) {
-                const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && S.has_a2;
-                for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {   // v[k] : 4 threads per column k, rows split by q
-                    double s = 0.0;
-                    if (k < n) {
-                        if (has1) for (int r = q; r < n; r += 4) s = fma(gL1[(size_t)i * nn + r * n + k], dnu[(i + 1) * n + r], s);
-                        if (has2) for (int r = q; r < n; r += 4) s = fma(gL2[(size_t)i * nn + r * n + k], dnu[(i + 2) * n + r], s);
+            const bool bw_smem = (NP > 32) && (n % 2 == 0) && (6 * nn <= 5 * G.blk()) && (FMPC_BW_SMEM != 0);
+            if (bw_smem) {
+                // The factor blocks of a stage (3 n^2 doubles) come back from the scratch through cp.async into the operand
+                // region, which is free now (6 buffers of n^2 doubles fit the five RP x ld blocks): stage i - 1 is in flight
+                // while stage i is consumed, and the GEMVs read shared memory instead of waiting on L2 for every element.
+                auto issue_stage = [&](int i, int buf) {
+                    const int h2 = (int)nn / 2;                   // 16-byte pieces per block (n even)
+                    for (int e = tid; e < 3 * h2; e += NTHREADS) {
+                        const int which = e / h2, off = 2 * (e - which * h2);
+                        const double *src = (which == 0 ? gL1 : (which == 1 ? gL2 : gLi)) + (size_t)i * nn + off;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(ops + (size_t)(buf * 3 + which) * nn + off);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                     }
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    if (k < n && q == 0) sm_rhs[k] = yv[i * n + k] - s;
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                };
+                double *dn1 = sm_y1, *dn2 = sm_y2;               // dnu_{i+1}, dnu_{i+2}
+                issue_stage(NB - 1, 0);
+                for (int i = NB - 1; i >= 0; --i) {
+                    const int buf = (NB - 1 - i) & 1;
+                    const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && S.has_a2;
+                    if (i > 0) { issue_stage(i - 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();
+                    const double *sL1 = ops + (size_t)(buf * 3) * nn, *sL2 = sL1 + nn, *sLi = sL2 + nn;
+                    for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {   // v[k] : 4 threads per column k, rows split by q
+                        double s = 0.0;
+                        if (k < n) {
+                            if (has1) for (int r = q; r < n; r += 4) s = fma(sL1[r * n + k], dn1[r], s);
+                            if (has2) for (int r = q; r < n; r += 4) s = fma(sL2[r * n + k], dn2[r], s);
+                        }
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        if (k < n && q == 0) sm_rhs[k] = yv[i * n + k] - s;
+                    }
+                    __syncthreads();
+                    for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {
+                        double s = 0.0;
+                        if (k < n) for (int r = k + q; r < n; r += 4) s = fma(sLi[r * n + k], sm_rhs[r], s);
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        if (k < n && q == 0) { dnu[i * n + k] = s; dn2[k] = s; }     // dn2 is dead: it becomes dnu_i
+                    }
+                    { double *t2 = dn1; dn1 = dn2; dn2 = t2; }       // (dnu_{i+1}, dnu_{i+2}) <- (dnu_i, dnu_{i+1})
+                    __syncthreads();
                 }
-                __syncthreads();
-                for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {
-                    double s = 0.0;
-                    if (k < n) for (int r = k + q; r < n; r += 4) s = fma(gLi[(size_t)i * nn + r * n + k], sm_rhs[r], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    if (k < n && q == 0) dnu[i * n + k] = s;
+            } else {
+                for (int i = NB - 1; i >= 0; --i) {
+                    const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && S.has_a2;
+                    for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {   // v[k] : 4 threads per column k, rows split by q
+                        double s = 0.0;
+                        if (k < n) {
+                            if (has1) for (int r = q; r < n; r += 4) s = fma(gL1[(size_t)i * nn + r * n + k], dnu[(i + 1) * n + r], s);
+                            if (has2) for (int r = q; r < n; r += 4) s = fma(gL2[(size_t)i * nn + r * n + k], dnu[(i + 2) * n + r], s);
+                        }
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        if (k < n && q == 0) sm_rhs[k] = yv[i * n + k] - s;
+                    }
+                    __syncthreads();
+                    for (int k = tid >> 2; k < RP; k += NTHREADS / 4) {
+                        double s = 0.0;
+                        if (k < n) for (int r = k + q; r < n; r += 4) s = fma(gLi[(size_t)i * nn + r * n + k], sm_rhs[r], s);
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        if (k < n && q == 0) dnu[i * n + k] = s;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
 
             // ---- dz = inv(Phi)(-r_d - C' dnu)  (:34-35) ----
