@@ -20,6 +20,7 @@
 //     n right-hand sides become DMMA products with inv(L)' and the substitutions become GEMVs.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "fmpc_internal.h"
 #include "fmpc_device.cuh"
@@ -28,16 +29,28 @@ using namespace fmpc_dev;
 
 namespace {
 
+#ifdef FMPC_PROF_BIG     /* phase timing of the n > 32 kernel: thread 0 of CTA 0, first instance, printed once */
+#define PB_DECL long long pb_acc[10] = {0,0,0,0,0,0,0,0,0,0}; long long pb_last = clock64();
+#define PB_T(idx) do { if (NP > 32 && tid == 0) { const long long now_ = clock64(); pb_acc[idx] += now_ - pb_last; pb_last = now_; } } while (0)
+#define PB_PRINT do { if (NP > 32 && tid == 0 && blockIdx.x == 0) printf("phase cycles: pre %lld gemmG %lld zero %lld ph1 %lld potrf %lld ph3 %lld back %lld dz %lld ls %lld rest %lld\n", pb_acc[0], pb_acc[1], pb_acc[2], pb_acc[3], pb_acc[4], pb_acc[5], pb_acc[6], pb_acc[7], pb_acc[8], pb_acc[9]); } while (0)
+#else
+#define PB_DECL
+#define PB_T(idx) do { } while (0)
+#define PB_PRINT do { } while (0)
+#endif
+#ifndef FMPC_BIG_THREADS
+#define FMPC_BIG_THREADS 256    // threads per CTA of the n > 32 kernel
+#endif
 #ifndef FMPC_BW_SMEM
 #define FMPC_BW_SMEM 0      // backward substitution of the n > 32 kernel with the factor blocks prefetched by cp.async into shared
                             // memory: parity-tested, but measured no faster on B200 at the C5 shape (51.5 k vs 49-53 k solves/s)
 #endif
-constexpr int MAXTT = 3;             // horizon (column) tiles accumulated together by one warp
+constexpr int MAXTT = 4;             // horizon (column) tiles accumulated together by one warp (T <= 32 in one pass)
 template <int NP> struct KCfg {
-    static constexpr int NTH = (NP > 32) ? 256 : 128;       // threads per CTA (9 warps for the 9 row tiles of a 72-row block measured no faster: registers)
+    static constexpr int NTH = (NP > 32) ? FMPC_BIG_THREADS : 128;       // threads per CTA (9 warps for the 9 row tiles of a 72-row block measured no faster: registers)
     static constexpr int MINB = (NP > 32) ? 1 : 5;          // resident CTAs per SM the register budget is set for
     static constexpr int KSMAX = (NP + 3) / 4;              // k-steps of a block product
-    static constexpr int RMAX = (NP > 32) ? 2 : 1;          // rows per 4-lane group in the GEMV phases
+    static constexpr int RMAX = (NP > 32 && FMPC_BIG_THREADS < 288) ? 2 : 1;          // rows per 4-lane group in the GEMV phases
 };
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b)
@@ -75,7 +88,7 @@ struct Geom {
         return (a + 1) & ~(size_t)1;
     }
     __host__ __device__ int vlen() const { return RP < 32 ? 32 : RP; }
-    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * 9 : 0); }
+    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * (FMPC_BIG_THREADS / 32) : 0); }
 };
 
 // C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory
@@ -567,7 +580,9 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
         __syncthreads();
 
         int status = ST_OK, iters = 0;
+        PB_DECL
         for (int it = 0; it < A.niters; ++it) {
+            PB_T(9);
             // ---- barrier terms (inf_newton_KKT_H.m:3-13), r_d (:12), p = inv(Phi) r_d staged for C p ----
             double ssd = 0.0;
             for (int e = tid; e < usp; e += NTHREADS) {
@@ -612,6 +627,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
             mma_apply_C(kc, rp, yv, true);
             __syncthreads();
 
+            PB_T(0);
             // ---- D_t = B diag(w_t) B' for all stages: Dsc(t, pair) = G * W ----
             for (int e = tid; e < usp; e += NTHREADS) {
                 const int t = e / ldp, j = e - t * ldp;
@@ -637,10 +653,12 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 }
             }
             __syncthreads();
+            PB_T(1);
             // zero the operand blocks (padding rows / columns must stay exactly zero)
             for (int e = tid; e < (int)(5 * G.blk()); e += NTHREADS) ops[e] = 0.0;
             __syncthreads();
 
+            PB_T(2);
             // ---- band-2 block Cholesky of Y fused with the forward solve (:30-31) ----
             // five blocks: Linv (doubles as S scratch), L1 ring x2, L2 ring x2 (the older one doubles as U scratch)
             double *bLinv = ops, *bM1 = ops + G.blk(), *bL1p = ops + 2 * G.blk();
@@ -697,6 +715,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                     if (q == 0) sm_rhs[r] = (r < n) ? yv[i * n + r] - s : 0.0;
                 }
                 __syncthreads();
+                PB_T(3);
                 // -- phase 2: factor + invert the diagonal block (one warp, rotating over the SM sub-partitions) --
                 if constexpr (NP > 32) {
                     const int info = cta_potrf_inverse(bS, bL2pp, ld, RP, gLi + (size_t)i * nn, n, tid, NTHREADS, ptmp, &s_info2);
@@ -710,6 +729,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 }
                 __syncthreads();
                 if (s_flag) { fail = true; break; }
+                PB_T(4);
                 // -- phase 3: L1_i = M1 inv(L)' (in place), L2_i = Y2 inv(L)' (into the dead L2pp block), y_i = inv(L) rhs --
                 double *bM2 = bL2pp;
                 for (int rt = wid; rt < nt; rt += NWARPS) {
@@ -794,6 +814,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                     double *t2 = bL2p; bL2p = bL2pp; bL2pp = t2;
                 }
                 __syncthreads();
+                PB_T(5);
             }
             if (fail) { status = ST_NOT_PD; break; }
 
@@ -868,12 +889,14 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 }
             }
 
+            PB_T(6);
             // ---- dz = inv(Phi)(-r_d - C' dnu)  (:34-35) ----
             stage_rows(kc, dnu, T, 0);
             __syncthreads();
             mma_apply_Ct<1>(kc, dnu, hdu, hdx, rdu, rdx, pinv, du, dx);
             __syncthreads();
 
+            PB_T(7);
             // ---- backtracking on ||[r_p; r_d]||, d frozen (backtracking_inf_newton.m:2-11) ----
             double t = 1.0;
             int nh = 0;
@@ -920,6 +943,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 t *= A.beta;
                 ++nh;
             }
+            PB_T(8);
             // accept: swap iterate / r_p buffers, advance the dual images
             { double *s1 = u; u = un; un = s1; double *s2 = x; x = xn; xn = s2; double *s3 = rp; rp = rpt; rpt = s3; }
             for (int e = tid; e < T * m; e += NTHREADS) hu[e] = __fma_rn(t, hdu[e], hu[e]);
@@ -937,6 +961,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
             if (A.status) A.status[b] = status;
             if (A.iters) A.iters[b] = iters;
             atomicAdd(A.iters_total, (unsigned long long)iters);
+            PB_PRINT;
         }
     }
 }
