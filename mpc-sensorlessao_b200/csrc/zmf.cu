@@ -319,7 +319,8 @@ cudaError_t zmf_launch_dmma(const zmf_handle *h, int nframes, const double *fram
 {
     constexpr int CH = ZChunk<NT>::CH;
     const size_t smem = (size_t)ZSTAGES * CH * NT * 64 * 8;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // the attribute is per device
+    bool &attr_done = attr_done_dev[h->device & 63];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -456,7 +457,8 @@ cudaError_t zmf_launch_synth(const zmf_handle *h, int nframes, const double *coe
 {
     constexpr int CH = (KS <= 9) ? 16 : 8, NW = 8;
     const size_t smem = (size_t)ZSTAGES * CH * KS * 32 * 8;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};          // the attribute is per device
+    bool &attr_done = attr_done_dev[h->device & 63];
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(zmf_synth_dmma_kernel<KS, MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
