@@ -1,0 +1,9 @@
+# compute-sanitizer passes over small instances of every kernel (memcheck: out-of-bounds / misaligned; racecheck: shared-memory hazards)
+set -x
+S="compute-sanitizer --error-exitcode 7 --print-limit 5"
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s301 or s304 or s306 or s308 or s310 or cold_start" 2>&1 | tail -4
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "s1_ or s7_ or s9_ or s14_ or s21_ or s23_ or s8_" 2>&1 | tail -4
+$S --tool memcheck python -m pytest tests/test_gpu_zernike.py tests/test_gpu_estimator.py tests/test_gpu_varid.py -m gpu -x -q -k "16-2 or 33-0 or 20-11 or 50-4 or 64-2 or other_shapes or 6-100 or 1-50 or synthesis_matches_basis" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "s23_ or s21_" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s310 or s305" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_zernike.py tests/test_gpu_varid.py -m gpu -x -q -k "16-2 or 64-2-130 or 16-12-3 or 1-50" 2>&1 | tail -4
