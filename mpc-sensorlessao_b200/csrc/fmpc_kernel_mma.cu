@@ -88,7 +88,7 @@ struct Geom {
         return (a + 1) & ~(size_t)1;
     }
     __host__ __device__ int vlen() const { return RP < 32 ? 32 : RP; }
-    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 64 + 64 * (FMPC_BIG_THREADS / 32) : 0); }
+    __host__ __device__ size_t smem_doubles() const { return ops_doubles() + (size_t)vlen() * 4 + 64 + 36 + (n > 32 ? 128 + 64 * (FMPC_BIG_THREADS / 32) : 0); }
 };
 
 // C(8x8 tile) += A(rows.., k) * B(rows.., k)'   over ksteps k-steps of 4, operands in shared memory
@@ -220,16 +220,79 @@ __device__ __forceinline__ int warp_potrf_inverse(const double *bS, double *bU, 
     return 0;
 }
 
+// 1/sqrt(x), x > 0 normal : MUFU.RSQ64H seed, one cubic (Halley) step and one quadratic polish -> last bit
+__device__ __forceinline__ double rsqrt_fast(const double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * e, fma(0.375, e, 0.5), y);
+    e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
+// One warp: Cholesky of the 8 x 8 diagonal tile kb of bS and its inverse, in registers (lane r & 7 owns row r, columns
+// travel by shuffles).  Rows / columns >= n behave as identity.  Writes inv(L_kk) to tLi (8 x 8 row-major) and to the
+// diagonal tile of bT.  Returns 0 or failing column + 1 (uniform over the warp).
+__device__ __forceinline__ int diag_tile_potrf_inverse(const double *bS, double *bT, int ld, int n, int kb, double *tLi, int lane)
+{
+    constexpr unsigned FULLM = 0xffffffffu;
+    const double *D = bS + (size_t)(8 * kb) * ld + 8 * kb;
+    const int r = lane & 7;
+    const bool rpad = (8 * kb + r >= n);
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = rpad ? ((c == r) ? 1.0 : 0.0) : ((c <= r) ? D[r * ld + c] : 0.0);
+    int info = 0;
+    double dinv = 1.0;                                          // 1 / L(r,r) = rsqrt of the r-th pivot
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double d = __shfl_sync(FULLM, a[k], k);
+        if ((!(d > 0.0) || !(d < 1.0e300)) && !info) info = 8 * kb + k + 1;       // uniform: same d in every lane
+        const double rs = rsqrt_fast(d);
+        if (r == k) dinv = rs;
+        const double l = a[k] * rs;                             // L(r,k) for r >= k (lane k: sqrt(d))
+        a[k] = l;
+#pragma unroll
+        for (int c = k + 1; c < 8; ++c) {
+            const double lc = __shfl_sync(FULLM, l, c);
+            if (r >= c) a[c] = fma(-l, lc, a[c]);
+        }
+    }
+    if (info) return info;
+    // inverse of the 8 x 8 lower factor: lane j (< 8) builds column j, rows of L arrive by shuffles
+    const int j = r;
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < i) sacc = fma(__shfl_sync(FULLM, a[k], i), x[k], sacc);
+        const double di = __shfl_sync(FULLM, dinv, i);
+        x[i] = (i < j) ? 0.0 : ((i == j) ? di : -sacc * di);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { tLi[i * 8 + j] = x[i]; bT[(size_t)(8 * kb + i) * ld + 8 * kb + j] = x[i]; }
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Whole CTA (n > 32): Cholesky of the n x n block in bS (lower triangle, leading dimension ld) and explicit inverse of
-// the factor, blocked by the 8 x 8 DMMA tile:
-//   for every block column kb:  warp 0 factors the diagonal tile (row per lane, shared memory) and inverts it;
-//                               panel rows  P = S[., kb] inv(L_kk)'  one thread per row;
-//                               trailing tiles  S[I,J] -= P_I P_J'  as DMMAs, one tile per warp task;
-//   inv(L) by block rows:       X[i,k] = -inv(L_ii) sum_{j=k}^{i-1} L[i,j] X[j,k]   (DMMAs; one (i,k) tile per warp),
-//                               X[k,k] = inv(L_kk) from the factorisation.
+// the factor, blocked by the 8 x 8 DMMA tile, right-looking with look-ahead:
+//   step kb:  warp 0 updates the next diagonal tile (kb+1, kb+1) and immediately factors / inverts it (registers,
+//             shuffles) while the other warps do the rest of the trailing update of step kb -- the serial diagonal
+//             tiles, not the tile products, are the critical path;
+//   a tile task (I, J), kb < J <= I, forms its two panel tiles P_I = S[I,kb] inv(L_kk)', P_J in accumulator layout
+//             (4 DMMAs) and multiplies them straight from registers: an accumulator tile {row gq, cols 2q, 2q+1} is a
+//             valid A operand and a valid B operand of X Y' with the contraction index taken as k = 2q + e.  Column kb
+//             of S is only read; the diagonal task (I, I) files the panel tile L[I,kb] at the mirrored (otherwise
+//             unused) upper position (kb, I);
+//   inv(L) by block columns: X[i,k] = -inv(L_ii) sum_{j=k}^{i-1} L[i,j] X[j,k], one warp per column, no CTA barrier.
 // Rows / columns >= n of the last tile behave as identity.  bT is a scratch block (receives X); on exit
-// bS <- inv(L) zero padded to RP x ld and gLinv <- n x n row-major.  tmp: 64 doubles per warp + 64.
+// bS <- inv(L) zero padded to RP x ld and gLinv <- n x n row-major.  tmp: 128 + 64 doubles per warp.
 // All threads must call it; returns 0 or failing column + 1 (the same value in every thread).
 // ---------------------------------------------------------------------------------------------
 __device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, int RP, double *gLinv, int n, int tid, int nth,
@@ -237,96 +300,64 @@ __device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, in
 {
     const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5, gq = lane >> 2, q = lane & 3;
     const int nt = RP / 8;
-    double *tLi = tmp;                                  // 8 x 8 inverse of the current diagonal tile
-    double *wtmp = tmp + 64 + 64 * wid;                 // per-warp 8 x 8 scratch
+    double *wtmp = tmp + 128 + 64 * wid;                // per-warp 8 x 8 scratch; tmp[0..127]: inv(L_kk), double buffered
     if (tid == 0) *s_info = 0;
-    for (int kb = 0; kb < nt; ++kb) {
-        __syncthreads();
-        if (wid == 0) {
-            // ---- diagonal tile in registers: lane r (< 8) owns row r, columns travel by shuffles ----
-            constexpr unsigned FULLM = 0xffffffffu;
-            const double *D = bS + (size_t)(8 * kb) * ld + 8 * kb;
-            const int r = lane & 7;
-            const bool rpad = (8 * kb + r >= n);
-            double a[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] = rpad ? ((c == r) ? 1.0 : 0.0) : ((c <= r) ? D[r * ld + c] : 0.0);
-            int info = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double d = __shfl_sync(FULLM, a[k], k);
-                if ((!(d > 0.0) || !(d < 1.0e300)) && !info) info = 8 * kb + k + 1;       // uniform: same d in every lane
-                const double l = a[k] * rsqrt(d);                                          // L(r,k) for r >= k (lane k: sqrt(d))
-                a[k] = l;
-#pragma unroll
-                for (int c = k + 1; c < 8; ++c) {
-                    const double lc = __shfl_sync(FULLM, l, c);
-                    if (r >= c) a[c] = fma(-l, lc, a[c]);
-                }
-            }
-            if (info) { if (lane == 0) *s_info = info; }
-            else {
-                // inverse of the 8 x 8 lower factor: lane j (< 8) builds column j, rows of L arrive by shuffles
-                double dg = a[0];
-#pragma unroll
-                for (int c = 1; c < 8; ++c) if (r == c) dg = a[c];
-                const double dinv = 1.0 / dg;
-                const int j = r;
-                double x[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (k < i) sacc = fma(__shfl_sync(FULLM, a[k], i), x[k], sacc);
-                    const double di = __shfl_sync(FULLM, dinv, i);
-                    x[i] = (i < j) ? 0.0 : ((i == j) ? di : -sacc * di);
-                }
-                if (lane < 8) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { tLi[i * 8 + j] = x[i]; bT[(size_t)(8 * kb + i) * ld + 8 * kb + j] = x[i]; }
-                }
-            }
-        }
-        __syncthreads();
-        if (*s_info) return *s_info;
-        // ---- panel: rows below the diagonal tile ----
-        for (int r = 8 * (kb + 1) + tid; r < RP; r += nth) {
-            double *row = bS + (size_t)r * ld + 8 * kb;
-            double x[8], y[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = row[k];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (k <= c) sacc = fma(x[k], tLi[c * 8 + k], sacc);
-                y[c] = sacc;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) row[k] = y[k];
-        }
-        __syncthreads();
-        // ---- trailing update: tiles (I, J), kb < J <= I ----
+    __syncthreads();
+    if (wid == 0) {
+        const int info = diag_tile_potrf_inverse(bS, bT, ld, n, 0, tmp, lane);
+        if (info && lane == 0) *s_info = info;
+    }
+    __syncthreads();
+    if (*s_info) return *s_info;
+    for (int kb = 0; kb + 1 < nt; ++kb) {
+        const double *tLi = tmp + 64 * (kb & 1);
         const int R = nt - kb - 1, ntask = R * (R + 1) / 2;
-        for (int task = wid; task < ntask; task += nw) {
+        auto tile_task = [&](int task) {
             int it = 0;
             while (task >= (it + 1) * (it + 2) / 2) ++it;
             const int jt = task - it * (it + 1) / 2;
             const int I = kb + 1 + it, J = kb + 1 + jt;
-            double p0 = 0.0, p1 = 0.0;
-            tile_nt(p0, p1, bS + (size_t)(8 * I + gq) * ld + 8 * kb + q, bS + (size_t)(8 * J + gq) * ld + 8 * kb + q, 2);
+            const double *Bl = tLi + gq * 8 + q;                 // B[k][n] = inv(L_kk)[n][k]
+            const double *Ai = bS + (size_t)(8 * I + gq) * ld + 8 * kb + q;
+            double pi0 = 0.0, pi1 = 0.0, pj0 = 0.0, pj1 = 0.0;
+            dmma(pi0, pi1, Ai[0], Bl[0]);
+            if (J != I) {
+                const double *Aj = bS + (size_t)(8 * J + gq) * ld + 8 * kb + q;
+                dmma(pj0, pj1, Aj[0], Bl[0]);
+                dmma(pi0, pi1, Ai[4], Bl[4]);
+                dmma(pj0, pj1, Aj[4], Bl[4]);
+            } else {
+                dmma(pi0, pi1, Ai[4], Bl[4]);
+                pj0 = pi0; pj1 = pi1;
+            }
+            double t0 = 0.0, t1 = 0.0;
+            dmma(t0, t1, pi0, pj0);
+            dmma(t0, t1, pi1, pj1);
             double *o = bS + (size_t)(8 * I + gq) * ld + 8 * J + 2 * q;
-            o[0] -= p0; o[1] -= p1;
+            o[0] -= t0; o[1] -= t1;
+            if (J == I) {
+                double *mo = bS + (size_t)(8 * kb + gq) * ld + 8 * I + 2 * q;
+                mo[0] = pi0; mo[1] = pi1;
+            }
+        };
+        if (wid == 0) {
+            tile_task(0);                                        // (kb+1, kb+1): the next diagonal tile ...
+            __syncwarp();
+            const int info = diag_tile_potrf_inverse(bS, bT, ld, n, kb + 1, tmp + 64 * ((kb + 1) & 1), lane);   // ... factored at once
+            if (info && lane == 0) *s_info = info;
+        } else {
+            for (int task = wid; task < ntask; task += nw - 1) tile_task(task);
         }
+        __syncthreads();
+        if (*s_info) return *s_info;
     }
-    __syncthreads();
-    // ---- inv(L) by block rows ----
-    for (int i = 1; i < nt; ++i) {
-        for (int k = wid; k < i; k += nw) {
+    // ---- inv(L) by block columns: column k is an independent forward substitution over its block rows, one warp per
+    //      column and no CTA barrier inside (L[i,j] is read from the mirrored tile (j, i)) ----
+    for (int k = wid; k + 1 < nt; k += nw) {
+        for (int i = k + 1; i < nt; ++i) {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
             for (int j = k; j < i; ++j) {
-                const double *Ap = bS + (size_t)(8 * i + gq) * ld + 8 * j + q;
+                const double *Ap = bS + (size_t)(8 * j + gq) * ld + 8 * i + q;
                 const double *Bp = bT + (size_t)(8 * j + q) * ld + 8 * k + gq;
                 dmma(c0, c1, Ap[0], Bp[0]);
                 dmma(e0, e1, Ap[4], Bp[(size_t)4 * ld]);
@@ -341,9 +372,10 @@ __device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, in
             dmma(x0, x1, Lp[4], wtmp[(4 + q) * 8 + gq]);
             double *o = bT + (size_t)(8 * i + gq) * ld + 8 * k + 2 * q;
             o[0] = -x0; o[1] = -x1;
+            __syncwarp();
         }
-        __syncthreads();
     }
+    __syncthreads();
     for (int e = tid; e < RP * ld; e += nth) {
         const int i = e / ld, j = e - i * ld;
         const double v = (i < n && j <= i) ? bT[e] : 0.0;
