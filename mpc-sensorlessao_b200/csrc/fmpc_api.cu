@@ -88,6 +88,8 @@ struct fmpc_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // host-buffer entry points: copy-in / solve / copy-out of successive instance chunks overlap on three streams
     static constexpr int MAX_CHUNKS = 32, MAX_PART = 4;
+    bool other_blocks_dirty = false;      // counter blocks 1.. hold totals of a multi-chunk call
+    int smid_slots = 0;                   // warp kernel: scratch slots indexed by SM id -> chunk kernels of one call may overlap freely
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaStream_t s_k[MAX_PART] = {};      // solve streams: partition p of the SMs / scratch slots runs chunks p, p + NP, ...
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
@@ -388,8 +390,9 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     if (ok) {
         h->ws_stride = h->cfg.ws_stride;
         const size_t wsb = (size_t)h->cfg.slots * h->cfg.ws_stride * sizeof(double);
-        if (h->ws.ensure(wsb) || h->counters.ensure(256 * fmpc_handle::MAX_PART)) ok = false;
-        if (ok && cudaMemset(h->counters.p, 0, 256 * fmpc_handle::MAX_PART) != cudaSuccess) ok = false;
+        if (h->ws.ensure(wsb) || h->counters.ensure(256 * fmpc_handle::MAX_CHUNKS)) ok = false;
+        if (ok && cudaMemset(h->counters.p, 0, 256 * fmpc_handle::MAX_CHUNKS) != cudaSuccess) ok = false;
+        if (ok && h->cfg.use_mma == 2 && !getenv("FMPC_NO_SMID_SLOTS")) h->smid_slots = fmpc_warp_smid_slots_ok(h->cfg, device);
         // the warp kernel relies on never-written padding columns of its scratch staying zero
         if (ok && cudaMemset(h->ws.p, 0, wsb) != cudaSuccess) ok = false;
     }
@@ -436,9 +439,10 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
     cudaSetDevice(h->device);
     unsigned long long v = 0;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
-    for (int p = 0; p < fmpc_handle::MAX_PART; ++p) {
-        unsigned long long vp = 0;
+    for (int p = 0; p < fmpc_handle::MAX_PART; ++p)
         if (cudaStreamSynchronize(h->s_k[p]) != cudaSuccess) return -1;
+    for (int p = 0; p < fmpc_handle::MAX_CHUNKS; ++p) {       // one counter block per (possibly concurrent) chunk launch
+        unsigned long long vp = 0;
         if (cudaMemcpy(&vp, h->counters.as<char>() + 256 * p + 8, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         v += vp;
     }
@@ -448,7 +452,7 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
 static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
                        const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
                        double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false,
-                       int part = 0, int nparts = 1)
+                       int part = 0, int nparts = 1, bool by_smid = false)
 {
     StepArgs A{};
     A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
@@ -461,12 +465,16 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     A.counter = (unsigned int *)cblk;
     A.iters_total = (unsigned long long *)(cblk + 8);
     SolveLaunchCfg cfg = h->cfg;
-    if (nparts > 1) { cfg.grid = h->cfg.grid / nparts; A.slot_base = part * cfg.grid; }
+    if (by_smid) A.slot_base = -1;                              // `part` only selects the counter block
+    else if (nparts > 1) { cfg.grid = h->cfg.grid / nparts; A.slot_base = part * cfg.grid; }
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     A.prof = (long long *)(h->counters.as<char>() + 64);
     CU_OK(cudaMemsetAsync(cblk, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
-    if (!keep_totals && nparts == 1 && part == 0)                    // a whole-grid launch starts a new total: clear the other partitions'
-        CU_OK(cudaMemsetAsync(h->counters.as<char>() + 256, 0, 256 * (fmpc_handle::MAX_PART - 1), st));
+    if (!keep_totals && nparts == 1 && part == 0 && h->other_blocks_dirty) {   // a whole-grid launch starts a new total
+        CU_OK(cudaMemsetAsync(h->counters.as<char>() + 256, 0, 256 * (fmpc_handle::MAX_CHUNKS - 1), st));
+        h->other_blocks_dirty = false;
+    }
+    if (part > 0) h->other_blocks_dirty = true;
     if (h->cfg.use_mma == 3) {
         if (nbatch > h->max_batch) return FMPC_ERR_BATCH;     // its scratch is sized by max_batch
         fmpc_launch_solve_gen(h->S, h->G, A, h->cfg, st);
@@ -528,6 +536,10 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     // own solve stream: chunk c runs as one wave on partition c % NP, so NP chunk kernels are resident side by side and the
     // pipeline fill / drain is a 1/NP-wave chunk instead of a whole wave.  With pageable host memory the copies degrade to
     // staged synchronous ones; the results are the same.
+    // SM-id scratch slots: chunk kernels need no SM partitions -- each chunk is launched on the next of MAX_PART streams with
+    // its own counter block and a grid of its own size, and the hardware packs the CTAs of overlapping chunks onto whatever
+    // SMs are free (no idle tail between the chunks of a partition).
+    const bool smid_mode = h->smid_slots && nb > (size_t)h->cfg.slots / 2 && !getenv("FMPC_STEP_PARTS");
     int NP = 1;
     // measured (profiles/r01_v3_7_e2e_partitions.log): 2 partitions beat 1 and 4 -- the host->device copies of a step
     // (133 MB at C2) take nearly as long as its solves, so finer chunks only add per-copy overhead
@@ -535,13 +547,18 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     if (const char *e = getenv("FMPC_STEP_PARTS")) { const int v = atoi(e); if (v >= 1 && v <= fmpc_handle::MAX_PART && h->cfg.use_mma == 2) NP = v; }
     const size_t wave = (NP > 1) ? (size_t)(h->cfg.grid / NP) * (size_t)(h->cfg.block / 32) : (size_t)h->cfg.slots;
     size_t per = wave;
+    if (smid_mode) {
+        per = (size_t)h->cfg.slots / 2;
+        if (const char *e = getenv("FMPC_STEP_CHUNK")) { const long v = atol(e); if (v >= 32) per = (size_t)v; }
+    }
     int nch = (int)((nb + per - 1) / per);
     if (NP == 1) { nch = (int)((nb + wave / 2) / wave); if (nch < 1) nch = 1; }
-    while (nch > fmpc_handle::MAX_CHUNKS) { per += wave; nch = (int)((nb + per - 1) / per); }
+    while (nch > fmpc_handle::MAX_CHUNKS) { per += smid_mode ? (size_t)h->cfg.slots / 2 : wave; nch = (int)((nb + per - 1) / per); }
     if (NP == 1) per = (nb + nch - 1) / nch;
     cudaStream_t si = h->s_in, so = h->s_out;
     const size_t Tn = (size_t)T * n, Tm = (size_t)T * m;
     while (nch > 1 && (size_t)(nch - 1) * per >= nb) --nch;           // no empty trailing chunk
+    if (smid_mode) CU_OK(cudaMemsetAsync(h->counters.p, 0, 256 * fmpc_handle::MAX_CHUNKS, si));   // every chunk's counter block, ahead of all chunks
     // the per-instance vectors are small: one copy each for the whole batch, ahead of the chunked arrays
     CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, si));
     if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, si));
@@ -552,8 +569,8 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     for (int ci = 0; ci <= nch; ++ci) {
         if (ci < nch) {
             const size_t b0 = (size_t)ci * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
-            const int part = ci % NP;
-            cudaStream_t sk = (NP > 1) ? h->s_k[part] : st;
+            const int part = smid_mode ? ci : ci % NP;
+            cudaStream_t sk = smid_mode ? h->s_k[ci % fmpc_handle::MAX_PART] : ((NP > 1) ? h->s_k[part] : st);
             if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, w + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
             if (X0) {
                 CU_OK(cudaMemcpyAsync(h->d_X.as<double>() + b0 * Tn, X0 + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
@@ -567,10 +584,10 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
                              (u_prev && h->ramp) ? h->d_uprev.as<double>() + b0 * m : nullptr, w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
                              X0 ? h->d_X.as<double>() + b0 * Tn : nullptr, X0 ? h->d_U.as<double>() + b0 * Tm : nullptr,
                              h->d_nu0.as<double>() + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
-                             h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, sk, ci >= NP, part, NP);
+                             h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, sk, smid_mode ? true : ci >= NP, part, NP, smid_mode);
             if (rc) return rc;
             CU_OK(cudaEventRecord(h->ev_k[ci], sk));
-            if (NP > 1) CU_OK(cudaStreamWaitEvent(st, h->ev_k[ci], 0));      // st collects every chunk (ev1, final sync)
+            if (NP > 1 || smid_mode) CU_OK(cudaStreamWaitEvent(st, h->ev_k[ci], 0));      // st collects every chunk (ev1, final sync)
         }
         if (ci >= 1) {
             const int cj = ci - 1;

@@ -45,7 +45,9 @@ struct StepArgs {
     unsigned long long *iters_total;    // sum of Newton iterations (zeroed before launch)
     double *ws;                         // per-slot scratch (slot = CTA for the CTA kernels, warp for the warp kernel)
     size_t ws_stride;                   // doubles per slot
-    int slot_base;                      // first CTA-slot of this launch (concurrent launches of one handle use disjoint slot ranges)
+    int slot_base;                      // first CTA-slot of this launch; -1: the CTA's scratch slot is its SM id (%smid), so that
+                                        // any number of concurrent launches of one handle share the per-SM scratch without
+                                        // collisions (at most one CTA of this kernel fits an SM)
     long long *prof;                    // optional phase-cycle accumulators (builds with -DFMPC_PROF), else NULL
 };
 
@@ -109,6 +111,7 @@ void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunch
 // kernel_warp.cu : warp-per-instance DMMA path (n <= 32), the default
 int  fmpc_warp_config(const DevSys &S, int device, SolveLaunchCfg *cfg);         // 0 ok, <0 not applicable
 void fmpc_launch_solve_warp(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);
+int  fmpc_warp_smid_slots_ok(const SolveLaunchCfg &cfg, int device);            // 1 if scratch slots may be indexed by %smid
 
 // kernel_gen.cu : general-structure path (VAR_1 ramp rows, literal VAR_1 column placement, dense Q / Qf)
 struct fmpc_sys;

@@ -1264,7 +1264,13 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
     c.kappa = A.kappa;
     c.smem = smem; c.oA1 = (int)(sA1 - smem); c.oA2 = (int)(sA2 - smem); c.oU = (int)(sUmax - smem); c.oQ = (int)(sQ2 - smem);
     c.wsm = smem + G.const_doubles + (size_t)wid * G.warp_doubles; c.BLK = G.BLK;
-    double *ws = A.ws + ((size_t)(A.slot_base + blockIdx.x) * nwarps + wid) * A.ws_stride;
+    // scratch slot: slot_base + blockIdx.x, or the SM id when slot_base < 0 (branch-free: the kernel sits at the register
+    // limit and an extra branch in the prologue measurably perturbs the allocation of the hot loops)
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned bysm = (unsigned)(A.slot_base >> 31);            // all ones iff slot_base < 0
+    const unsigned slot = (smid & bysm) | ((unsigned)(A.slot_base + (int)blockIdx.x) & ~bysm);
+    double *ws = A.ws + ((size_t)slot * nwarps + wid) * A.ws_stride;
     c.ws = ws; c.tu = G.TP8 * G.mpad; c.tx = G.TP8 * npad; c.tb = (G.TP8 + 1) * npad; c.bl = (T + 1) * G.NN; c.pp = 0;
     c.ypool = S.ypool; c.ydi = S.ydi; c.y1i = S.y1i; c.y2i = S.y2i;
     c.xmin = S.xmin; c.xmax = S.xmax;
@@ -1470,6 +1476,23 @@ int fmpc_warp_config(const DevSys &S, int device, SolveLaunchCfg *cfg)
     WARP_DISPATCH(G, CALL_CFG)
 #undef CALL_CFG
     return rc;
+}
+
+namespace { __global__ void fmpc_nsmid_kernel(unsigned *out) { unsigned v; asm("mov.u32 %0, %%nsmid;" : "=r"(v)); *out = v; } }
+
+// Scratch slots may be indexed by the SM id when SM ids are dense below the slot count and two CTAs can never share an SM
+// (each needs more than half of its shared memory).
+int fmpc_warp_smid_slots_ok(const SolveLaunchCfg &cfg, int device)
+{
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
+    if (2 * (cfg.smem + 1024) <= (size_t)prop.sharedMemPerMultiprocessor) return 0;
+    unsigned *d = nullptr, nsmid = 0;
+    if (cudaMalloc(&d, 4) != cudaSuccess) return 0;
+    fmpc_nsmid_kernel<<<1, 1>>>(d);
+    const bool ok = cudaMemcpy(&nsmid, d, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d);
+    return ok && nsmid > 0 && (int)nsmid <= cfg.grid;
 }
 
 void fmpc_launch_solve_warp(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream)
