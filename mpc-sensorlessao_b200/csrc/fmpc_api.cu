@@ -742,39 +742,54 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, co
     const size_t nb = (size_t)nbatch, n = h->n, m = h->m, T = h->T, NBn = T * n;
     cudaStream_t st = h->stream;
     if (h->d_x0.ensure(nb * n * 8) || h->d_x0pre.ensure(nb * n * 8) || h->d_uprev.ensure(nb * m * 8) ||
-        h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
+        h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(2 * nb * NBn * 8) ||
         h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4) || h->d_a.ensure(nb * n * K * 8) ||
         h->d_Uacc.ensure(nb * m * K * 8) || h->d_Xacc.ensure(nb * n * K * 8) || h->d_itacc.ensure(nb * K * 4))
         return FMPC_ERR_CUDA;
+    cudaStream_t si = h->s_in;
     CU_OK(cudaMemcpyAsync(h->d_a.p, a, nb * n * K * 8, cudaMemcpyHostToDevice, st));
     CU_OK(cudaMemsetAsync(h->d_x0.p, 0, nb * n * 8, st));
     CU_OK(cudaEventRecord(h->ev0, st));
-    for (int k = 0; k < K; ++k) {
+    // The dual start of step k + 1 is uploaded on the copy stream (two device buffers) while the solve of step k runs: with
+    // pageable host memory that copy blocks the calling thread, not the GPU.  ev_in[b]: buffer b filled; ev_k[b]: buffer b consumed.
+    auto upload_nu = [&](int k) -> int {
+        const int buf = k & 1;
         const double *nu_src;
         if (nu0) nu_src = nu0 + (size_t)k * nb * NBn;
-        else {
+        else {      // MATLAB default stream, one rand(length(b),1) per instance and step
             h->h_nu.resize(nb * NBn);
             for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
             nu_src = h->h_nu.data();
-            CU_OK(cudaStreamSynchronize(st));     // h_nu is reused next step
         }
-        CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, st));
+        if (k >= 2) CU_OK(cudaStreamWaitEvent(si, h->ev_k[buf], 0));       // the solve of step k - 2 has read this buffer
+        CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + (size_t)buf * nb * NBn, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, si));
+        CU_OK(cudaEventRecord(h->ev_in[buf], si));
+        if (!nu0) CU_OK(cudaStreamSynchronize(si));                        // h_nu is overwritten for the next step
+        return FMPC_OK;
+    };
+    rc = upload_nu(0);
+    if (rc) return rc;
+    for (int k = 0; k < K; ++k) {
+        const int buf = k & 1;
         // x0 = a[:,k,b] + B u_prev ; x0_pre <- previous x0 ; warm start shifted one stage
         fmpc_launch_shift_warm(h->S, nbatch, h->d_a.as<double>() + (size_t)k * n, (int)(n * K), h->d_X.as<double>(),
                                h->d_U.as<double>(), h->d_x0.as<double>(), h->d_x0pre.as<double>(), h->d_uprev.as<double>(),
                                k == 0, st);
         CU_OK(cudaGetLastError());
         h->launches += 1;
+        CU_OK(cudaStreamWaitEvent(st, h->ev_in[buf], 0));
         rc = step_device(h, p, nbatch, h->d_x0.as<double>(), h->d_x0pre.as<double>(), h->d_uprev.as<double>(), nullptr, nullptr,
-                         k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(), h->d_nu0.as<double>(),
+                         k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(),
+                         h->d_nu0.as<double>() + (size_t)buf * nb * NBn,
                          h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
         if (rc) return rc;
-        // logs: U_acc[:,k,b] = U(:,0,b), X_acc[:,k,b] = x0
-        CU_OK(cudaMemcpy2DAsync(h->d_Uacc.as<double>() + (size_t)k * m, m * K * 8, h->d_U.p, m * T * 8, m * 8, nb,
-                                cudaMemcpyDeviceToDevice, st));
-        CU_OK(cudaMemcpy2DAsync(h->d_Xacc.as<double>() + (size_t)k * n, n * K * 8, h->d_x0.p, n * 8, n * 8, nb,
-                                cudaMemcpyDeviceToDevice, st));
-        CU_OK(cudaMemcpy2DAsync(h->d_itacc.as<int>() + k, K * 4, h->d_iters.p, 4, 4, nb, cudaMemcpyDeviceToDevice, st));
+        CU_OK(cudaEventRecord(h->ev_k[buf], st));
+        // logs: U_acc[:,k,b] = U(:,0,b), X_acc[:,k,b] = x0, iters
+        fmpc_launch_log_step((int)n, (int)m, (int)T, nbatch, K, k, h->d_U.as<double>(), h->d_x0.as<double>(), h->d_iters.as<int>(),
+                             h->d_Uacc.as<double>(), h->d_Xacc.as<double>(), h->d_itacc.as<int>(), st);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+        if (k + 1 < K) { rc = upload_nu(k + 1); if (rc) return rc; }
     }
     CU_OK(cudaEventRecord(h->ev1, st));
     CU_OK(cudaMemcpyAsync(U_acc, h->d_Uacc.p, nb * m * K * 8, cudaMemcpyDeviceToHost, st));

@@ -104,6 +104,9 @@ void fmpc_launch_state_update(const DevSys &S, int nbatch, const double *x, cons
 void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int a_stride, double *X, double *U,
                             double *x0, double *x0_pre, double *u_prev, int first, void *stream);
 
+void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const double *U, const double *x0, const int *iters,
+                          double *Uacc, double *Xacc, int *itacc, void *stream);
+
 // kernel_mma.cu : CTA-per-instance DMMA path (n <= 72)
 int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable
 void fmpc_launch_solve_mma(const DevSys &S, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream);

@@ -386,6 +386,21 @@ __global__ void fmpc_shift_warm_kernel(const DevSys S, int nbatch, const double 
     }
 }
 
+// closed-loop logs of step k: U_acc[:,k,b] = U(:,0,b) (the applied input), X_acc[:,k,b] = x0[:,b], iters_acc[k,b] = iters[b]
+__global__ void fmpc_log_step_kernel(int n, int m, int T, int nbatch, int K, int k, const double *__restrict__ U,
+                                     const double *__restrict__ x0, const int *__restrict__ iters, double *__restrict__ Uacc,
+                                     double *__restrict__ Xacc, int *__restrict__ itacc)
+{
+    const size_t tot = (size_t)nbatch * (m + n);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / (m + n);
+        const int j = (int)(e - b * (m + n));
+        if (j < m) Uacc[(b * K + k) * m + j] = U[b * (size_t)m * T + j];
+        else Xacc[(b * K + k) * n + (j - m)] = x0[b * n + (j - m)];
+        if (j == 0 && itacc) itacc[b * K + k] = iters[b];
+    }
+}
+
 // =============================================================================================
 // host-side launch helpers
 // =============================================================================================
@@ -437,4 +452,14 @@ void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int 
     if (grid < 1) grid = 1;
     fmpc_shift_warm_kernel<<<grid, 64, (size_t)S.m * sizeof(double), (cudaStream_t)stream>>>(S, nbatch, a_k, a_stride, X, U,
                                                                                             x0, x0_pre, u_prev, first);
+}
+
+void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const double *U, const double *x0, const int *iters,
+                          double *Uacc, double *Xacc, int *itacc, void *stream)
+{
+    const size_t tot = (size_t)nbatch * (m + n);
+    int grid = (int)((tot + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    fmpc_log_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, T, nbatch, K, k, U, x0, iters, Uacc, Xacc, itacc);
 }
