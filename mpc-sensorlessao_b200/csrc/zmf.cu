@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT) zmf_fit_kernel(const double *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int ZSTAGES = 3;
+constexpr int ZSTAGES = 3;             // shared-memory stages of the operator (the fit kernel also has a 2-stage variant)
 template <int NT> struct ZChunk { static constexpr int CH = (NT <= 4) ? 16 : 8; };     // groups per shared-memory stage
 #ifndef ZMF_PF
 #define ZMF_PF 16
@@ -158,8 +158,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
     return ok != 0;
 }
 
-template <int NT, int MT, int NW, bool VEC>
-__global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__restrict__ Wf, const unsigned *__restrict__ ginfo, int ngroups,
+// ST = 3 stages, or ST = 2 with the register budget of three resident CTAs per SM (80 registers, 24 warps): measured faster for
+// large frame counts (32 768 frames: 1.15 vs 1.24 ms), slower for small ones
+template <int NT, int MT, int NW, bool VEC, int ST>
+__global__ void __launch_bounds__(NW * 32, ST == 2 ? 3 : 1) zmf_fit_dmma_kernel(const double *__restrict__ Wf, const unsigned *__restrict__ ginfo, int ngroups,
                                                                int groups_per_split, const double *__restrict__ frames,
                                                                double *__restrict__ out, int out_ld, size_t out_split_stride,
                                                                int npix, int nmodes, int nframes, const double *__restrict__ offv)
@@ -167,8 +169,8 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
     constexpr int CH = ZChunk<NT>::CH, GD = NT * 64;            // doubles of W per group
     constexpr int ZRING = ZRingDepth<MT>::V;
     static_assert(CH % ZRING == 0, "ring depth must divide the chunk");
-    extern __shared__ __align__(128) double wbuf[];             // ZSTAGES x CH x GD
-    __shared__ __align__(8) unsigned long long bars[ZSTAGES];
+    extern __shared__ __align__(128) double wbuf[];             // ST x CH x GD
+    __shared__ __align__(8) unsigned long long bars[ST];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
     const int g_begin = blockIdx.y * groups_per_split;
     const int g_end = min(ngroups, g_begin + groups_per_split);
@@ -176,18 +178,18 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
     const int f0 = (blockIdx.x * NW + warp) * 8 * MT;
 
     if (tid == 0) {
-        for (int s = 0; s < ZSTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        for (int s = 0; s < ST; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int c) {       // thread 0: chunk c of this split -> stage c % ZSTAGES
-        const int s = c % ZSTAGES, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
+    auto issue = [&](int c) {       // thread 0: chunk c of this split -> stage c % ST
+        const int s = c % ST, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
         const unsigned bytes = (unsigned)ng * GD * 8u, bar = smem_u32(&bars[s]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(wbuf + (size_t)s * CH * GD)), "l"(Wf + (size_t)g0 * GD), "r"(bytes), "r"(bar) : "memory");
     };
-    if (tid == 0) for (int c = 0; c < ZSTAGES && c < nch; ++c) issue(c);
+    if (tid == 0) for (int c = 0; c < ST && c < nch; ++c) issue(c);
 
     // frame rows of this lane (rows past the last frame alias the last one: loaded, never stored)
     const double *fr[MT];
@@ -225,8 +227,8 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
     for (int d = 0; d < ZRING; ++d) load_frames(d, rinfo[d]);
 
     for (int c = 0; c < nch; ++c) {
-        const int s = c % ZSTAGES;
-        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ZSTAGES) & 1);
+        const int s = c % ST;
+        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ST) & 1);
         while (!mbar_try_wait(bar, parity)) { }
         const double *wb = wbuf + (size_t)s * CH * GD + 2 * lane;
         const int g0 = g_begin + c * CH;
@@ -277,9 +279,9 @@ __global__ void __launch_bounds__(NW * 32) zmf_fit_dmma_kernel(const double *__r
             }
         }
         __syncthreads();                                 // every warp is done with stage s
-        if (tid == 0 && c + ZSTAGES < nch) {
+        if (tid == 0 && c + ST < nch) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(c + ZSTAGES);
+            issue(c + ST);
         }
     }
     double *o = out + (size_t)blockIdx.y * out_split_stride;
@@ -313,21 +315,21 @@ __global__ void zmf_reduce_kernel(const double *__restrict__ part, int ksplit, s
     }
 }
 
-template <int NT, int MT, int NW, bool VEC>
+template <int NT, int MT, int NW, bool VEC, int ST>
 cudaError_t zmf_launch_dmma(const zmf_handle *h, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
                             int ksplit, int gps, cudaStream_t st)
 {
     constexpr int CH = ZChunk<NT>::CH;
-    const size_t smem = (size_t)ZSTAGES * CH * NT * 64 * 8;
+    const size_t smem = (size_t)ST * CH * NT * 64 * 8;
     static bool attr_done_dev[64] = {};          // the attribute is per device
     bool &attr_done = attr_done_dev[h->device & 63];
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(zmf_fit_dmma_kernel<NT, MT, NW, VEC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     dim3 grid((nframes + NW * 8 * MT - 1) / (NW * 8 * MT), ksplit);
-    zmf_fit_dmma_kernel<NT, MT, NW, VEC><<<grid, NW * 32, smem, st>>>(h->d_Wf, h->d_ginfo, h->ngroups, gps, frames, out, out_ld, split_stride,
+    zmf_fit_dmma_kernel<NT, MT, NW, VEC, ST><<<grid, NW * 32, smem, st>>>(h->d_Wf, h->d_ginfo, h->ngroups, gps, frames, out, out_ld, split_stride,
                                                                       h->npix, h->nmodes, nframes, ksplit > 1 ? nullptr : h->d_off);
     return cudaGetLastError();
 }
@@ -336,9 +338,10 @@ template <int NT>
 cudaError_t zmf_launch_nt(const zmf_handle *h, int mt, int nframes, const double *frames, double *out, int out_ld, size_t split_stride,
                           int ksplit, int gps, cudaStream_t st)
 {
-    if (mt < 0) return zmf_launch_dmma<NT, 1, 8, false>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
-    if (mt == 2) return zmf_launch_dmma<NT, 2, 8, true>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
-    return zmf_launch_dmma<NT, 1, 8, true>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    if (mt < 0) return zmf_launch_dmma<NT, 1, 8, false, 3>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    if (mt == 3) return zmf_launch_dmma<NT, 2, 8, true, 2>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);   // large batches
+    if (mt == 2) return zmf_launch_dmma<NT, 2, 8, true, 3>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
+    return zmf_launch_dmma<NT, 1, 8, true, 3>(h, nframes, frames, out, out_ld, split_stride, ksplit, gps, st);
 }
 
 } // namespace
@@ -669,7 +672,8 @@ int zmf_fit_d(zmf_handle *h, int nframes, const double *frames, double *coef, vo
             out = h->d_part; out_ld = ld;
         }
         cudaError_t e = cudaErrorInvalidValue;
-        const int mtsel = vec ? mt : -1;
+        int mtsel = vec ? mt : -1;
+        if (mtsel == 2 && nframes > 8192 && !getenv("ZMF_NO_ST2")) mtsel = 3;     // 2-stage / 3-CTA variant
         switch (h->ntiles) {
         case 1: e = zmf_launch_nt<1>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
         case 2: e = zmf_launch_nt<2>(h, mtsel, nframes, frames, out, out_ld, stride, ksplit, gps, st); break;
