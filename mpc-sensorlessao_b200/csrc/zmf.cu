@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(NT) zmf_fit_kernel(const double *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int ZSTAGES = 3;             // shared-memory stages of the operator (the fit kernel also has a 2-stage variant)
+#ifndef ZSYN_STAGES
+#define ZSYN_STAGES 2      // measured (profiles/r01_zmf_occupancy.log): 2 stages (3 resident CTAs) beat 3 stages and 8-group chunks
+#endif
+#ifndef ZSYN_CH
+#define ZSYN_CH 16
+#endif
 template <int NT> struct ZChunk { static constexpr int CH = (NT <= 4) ? 16 : 8; };     // groups per shared-memory stage
 #ifndef ZMF_PF
 #define ZMF_PF 16
@@ -362,27 +367,27 @@ __global__ void __launch_bounds__(NW * 32) zmf_synth_dmma_kernel(const double *_
                                                                  int groups_per_split, const double *__restrict__ coef,
                                                                  double *__restrict__ frames, int npix, int nmodes, int nframes)
 {
-    constexpr int CH = (KS <= 9) ? 16 : 8, GD = KS * 32;
-    extern __shared__ __align__(128) double zbuf[];             // ZSTAGES x CH x GD
-    __shared__ __align__(8) unsigned long long bars[ZSTAGES];
+    constexpr int CH = (KS <= 9) ? ZSYN_CH : 8, GD = KS * 32;
+    extern __shared__ __align__(128) double zbuf[];             // ZSYN_STAGES x CH x GD
+    __shared__ __align__(8) unsigned long long bars[ZSYN_STAGES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, q = lane & 3;
     const int g_begin = blockIdx.y * groups_per_split;
     const int g_end = min(ngroups, g_begin + groups_per_split);
     const int nch = (g_end - g_begin + CH - 1) / CH;
     const int f0 = (blockIdx.x * NW + warp) * 8 * MT;
     if (tid == 0) {
-        for (int s = 0; s < ZSTAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
+        for (int s = 0; s < ZSYN_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     auto issue = [&](int c) {
-        const int s = c % ZSTAGES, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
+        const int s = c % ZSYN_STAGES, g0 = g_begin + c * CH, ng = min(CH, g_end - g0);
         const unsigned bytes = (unsigned)ng * GD * 8u, bar = smem_u32(&bars[s]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(zbuf + (size_t)s * CH * GD)), "l"(Zf + (size_t)g0 * GD), "r"(bytes), "r"(bar) : "memory");
     };
-    if (tid == 0) for (int c = 0; c < ZSTAGES && c < nch; ++c) issue(c);
+    if (tid == 0) for (int c = 0; c < ZSYN_STAGES && c < nch; ++c) issue(c);
 
     // A fragments: coef[frame f0 + 8 mt + gq][mode 4 s + q], zero beyond nmodes / nframes
     double a[MT][KS];
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__(NW * 32) zmf_synth_dmma_kernel(const double *_
         orow[mt] = frames + (size_t)min(f, nframes - 1) * npix + 2 * q;
     }
     for (int c = 0; c < nch; ++c) {
-        const int s = c % ZSTAGES;
-        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ZSTAGES) & 1);
+        const int s = c % ZSYN_STAGES;
+        const unsigned bar = smem_u32(&bars[s]), parity = (unsigned)((c / ZSYN_STAGES) & 1);
         while (!mbar_try_wait(bar, parity)) { }
         const double *zb = zbuf + (size_t)s * CH * GD + lane;
         const int g0 = g_begin + c * CH;
@@ -431,9 +436,9 @@ __global__ void __launch_bounds__(NW * 32) zmf_synth_dmma_kernel(const double *_
             }
         }
         __syncthreads();
-        if (tid == 0 && c + ZSTAGES < nch) {
+        if (tid == 0 && c + ZSYN_STAGES < nch) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(c + ZSTAGES);
+            issue(c + ZSYN_STAGES);
         }
     }
 }
@@ -458,8 +463,8 @@ __global__ void zmf_synth_kernel(const double *__restrict__ Z, const unsigned ch
 template <int KS, int MT>
 cudaError_t zmf_launch_synth(const zmf_handle *h, int nframes, const double *coef, double *frames, int ksplit, int gps, cudaStream_t st)
 {
-    constexpr int CH = (KS <= 9) ? 16 : 8, NW = 8;
-    const size_t smem = (size_t)ZSTAGES * CH * KS * 32 * 8;
+    constexpr int CH = (KS <= 9) ? ZSYN_CH : 8, NW = 8;
+    const size_t smem = (size_t)ZSYN_STAGES * CH * KS * 32 * 8;
     static bool attr_done_dev[64] = {};          // the attribute is per device
     bool &attr_done = attr_done_dev[h->device & 63];
     if (!attr_done) {
