@@ -28,6 +28,11 @@ namespace {
 
 constexpr int GEN_THREADS = 256;
 
+__device__ __forceinline__ void dmma_gen(double &c0, double &c1, const double a, const double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 struct GenWs {      // per-CTA scratch layout (doubles)
     size_t z, zt, dz, rd, h, hd, pd, nu, dnu, rp, rpt, bv, yv, tdiag, toff, minv, Y, total;
     __host__ __device__ static GenWs make(int n, int m, int T, int ramp)
@@ -274,26 +279,50 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             for (int e = tid; e < NE; e += nt) yv[e] = rp[e] - yv[e];
 
             // ---- Y = Yx + C_u inv(Phi_uu) C_u'  (lower block triangle, full diagonal blocks) ----
-            for (int i = 0; i < NB; ++i)
-                for (int k = 0; k <= i; ++k)
-                    for (int e = tid; e < n * n; e += nt) {
-                        const int r = e / n, c = e - r * n;
-                        double acc = __ldg(G.Yx + ((size_t)i * n + r) * G.ldyx + (size_t)k * n + c);
-                        for (int a = 0; a < G.ue_cnt[i]; ++a) {
-                            const int ta = G.ue_t[4 * i + a];
-                            const double *Ca = G.cu + G.ue_ptr[4 * i + a] + (size_t)r * m;
-                            for (int bb = 0; bb < G.ue_cnt[k]; ++bb) {
-                                const int tb = G.ue_t[4 * k + bb];
-                                if (!G.ramp && ta != tb) continue;
-                                const double *cv = G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m;
-                                const double *Cbt = G.cut + G.ue_ptr[4 * k + bb] + c;
-                                double s = 0.0;
-                                for (int j = 0; j < m; ++j) s = fma(__ldg(Ca + j) * cv[j], __ldg(Cbt + (size_t)j * n), s);
-                                acc += s;
+            // One warp task per (block pair, 8 x 8 tile): the tile of  sum_ab C_a diag(cv_ab) C_b'  is a chain of FP64 tensor-pipe
+            // products over the m actuators (A = C_a[r][j] cv[j] scaled on the fly, B = C_b[c][j], both L1-resident).
+            {
+                const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5, gq = lane >> 2, q = lane & 3;
+                const int ntl = (n + 7) / 8, npair = NB * (NB + 1) / 2, ntask = npair * ntl * ntl;
+                for (int task = wid; task < ntask; task += nw) {
+                    const int pr = task / (ntl * ntl), tl = task - pr * ntl * ntl, rt = tl / ntl, ct = tl - rt * ntl;
+                    int i = 0;
+                    while ((i + 1) * (i + 2) / 2 <= pr) ++i;
+                    const int k = pr - i * (i + 1) / 2;
+                    const int ra = 8 * rt + gq, cb = 8 * ct + gq;             // A-operand row / B-operand row of this lane
+                    double c0 = 0.0, c1 = 0.0;
+                    for (int a = 0; a < G.ue_cnt[i]; ++a) {
+                        const int ta = G.ue_t[4 * i + a];
+                        const double *Ca = G.cu + G.ue_ptr[4 * i + a] + (size_t)min(ra, n - 1) * m;
+                        for (int bb = 0; bb < G.ue_cnt[k]; ++bb) {
+                            const int tb = G.ue_t[4 * k + bb];
+                            if (!G.ramp && ta != tb) continue;
+                            const double *cv = G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m;
+                            const double *Cb = G.cu + G.ue_ptr[4 * k + bb] + (size_t)min(cb, n - 1) * m;
+                            double e0 = 0.0, e1 = 0.0;
+                            int jb = 0;                                       // warp-uniform loop bounds (mma.sync needs all lanes)
+                            for (; jb + 8 <= m; jb += 8) {                    // two accumulation chains
+                                const int j = jb + q;
+                                dmma_gen(c0, c1, __ldg(Ca + j) * cv[j], __ldg(Cb + j));
+                                dmma_gen(e0, e1, __ldg(Ca + j + 4) * cv[j + 4], __ldg(Cb + j + 4));
                             }
+                            for (; jb < m; jb += 4) {                         // remaining k-steps, columns >= m contribute zeros
+                                const int j = jb + q;
+                                const bool ok = j < m;
+                                dmma_gen(c0, c1, ok ? __ldg(Ca + j) * cv[j] : 0.0, ok ? __ldg(Cb + j) : 0.0);
+                            }
+                            c0 += e0; c1 += e1;
                         }
-                        Y[((size_t)i * n + r) * ldy + (size_t)k * n + c] = acc;
                     }
+                    const int r = 8 * rt + gq, c = 8 * ct + 2 * q;
+                    if (r < n) {
+                        const double *yx = G.Yx + ((size_t)i * n + r) * G.ldyx + (size_t)k * n;
+                        double *yo = Y + ((size_t)i * n + r) * ldy + (size_t)k * n;
+                        if (c < n) yo[c] = __ldg(yx + c) + c0;
+                        if (c + 1 < n) yo[c + 1] = __ldg(yx + c + 1) + c1;
+                    }
+                }
+            }
             __syncthreads();
 
             // ---- dense blocked Cholesky of Y fused with the forward substitution (:30-31) ----
