@@ -75,3 +75,36 @@ def test_product_path_never_imports_the_oracle():
                 src = open(os.path.join(dp_, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "fmpc_ref" not in src and "fref_" not in src, f
+
+
+def test_var1_mirror_is_the_reference_problem_by_default(pk):
+    """Fast_MPC2_VAR1 = VAR_1/Fast_MPC2.m: 21 ctor arguments, ramp rows + literal C unless switched off; the ramp
+    rows need u_prev and du bounds of size m (VAR_1/fast_mpc_ineq_const.m:72-74)."""
+    n, m, T = 3, 2, 4
+    args = [np.eye(n), np.eye(m), None, np.eye(n), None, None, None, -np.ones(n), np.ones(n), -np.ones(m), np.ones(m),
+            -0.1 * np.ones(m), 0.1 * np.ones(m), T, np.zeros(n), np.zeros(m), 0.5 * np.eye(n), np.ones((n, m)), np.zeros(T * n), None, None]
+    o = pk.Fast_MPC2_VAR1(*args)
+    assert o._ramp_rows and o._literal_bug and o.var_order == 1
+    assert o._validate() == (n, m)
+    bad = list(args); bad[15] = None                      # u_prev = []
+    with pytest.raises(ValueError, match="incompatible sizes"):
+        pk.Fast_MPC2_VAR1(*bad)._validate()
+    bad = list(args); bad[11] = np.ones(m + 1)            # du_min of the wrong size
+    with pytest.raises(ValueError, match="cotrol iequality"):
+        pk.Fast_MPC2_VAR1(*bad)._validate()
+    assert pk.Fast_MPC2_VAR1(*bad, ramp_rows=False, literal_bug=False)._validate() == (n, m)
+
+
+def test_side_entry_points_validate_before_cuda(pk):
+    """Argument errors of the estimator / identification entry points carry their own codes even without a GPU."""
+    with pytest.raises(pk.FmpcError) as e:
+        pk.Estimator(np.zeros((3, 5)))                    # more modes than pixels
+    assert e.value.code == -2
+    with pytest.raises(ValueError, match="incompatible sizes"):
+        pk.Estimator(np.ones((6, 2)), np.ones(5))
+    with pytest.raises(pk.FmpcError) as e:
+        pk.identify_var(np.zeros((10, 8)), 2)             # fewer equations than unknowns
+    assert e.value.code == -2
+    with pytest.raises(pk.FmpcError) as e:
+        pk.identify_var(np.zeros((600, 45)), 2)           # accumulators exceed the kernel's budget
+    assert e.value.code == -2
