@@ -117,6 +117,23 @@ def bench_c1(K=200):
     dt = (time.perf_counter() - t0) / nst
     print(json.dumps({"cpu_baseline": {"kind": "port", "what": "literal dense numpy restatement of Fast_MPC/VAR_1 (what MATLAB executes)",
                                        "steps_per_s": 1 / dt, "cores": os.cpu_count(), "sample": f"{nst} closed-loop steps"}}), flush=True)
+    # structured C port (oracle/fmpc_ref_general.c) on the same loop, one instance = one host thread
+    from oracle import fmpc_ref
+    u_prev = np.zeros(p.m); z = np.tile(np.concatenate([(p.u_min + p.u_max) / 2, (p.x_min + p.x_max) / 2]), p.T)
+    t0 = time.perf_counter(); nst2 = 10
+    for k in range(nst2):
+        x0 = a[0, k] + p.B @ u_prev
+        if k > 0:
+            Z = z.reshape(p.T, p.n + p.m); z = np.vstack([Z[1:], Z[-1:]]).reshape(-1)
+        out = fmpc_ref.solve_batch_general(p.A1, None, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, 0.01, 5, x0[:, None], None, None,
+                                           z[:, None], nu0[k, 0][:, None], u_prev=u_prev[:, None], du_min=p.du_min, du_max=p.du_max,
+                                           ramp_rows=True, literal_bug=True)
+        z = out["z"][:, 0].copy(); u_prev = z[:p.m].copy()
+        if k < 3:
+            print(f"  step {k}: C port relerr(U applied) {np.abs(first['U_acc'][0, k] - u_prev).max() / np.abs(u_prev).max():.2e}", flush=True)
+    dt2 = (time.perf_counter() - t0) / nst2
+    print(json.dumps({"cpu_baseline": {"kind": "port", "what": "structured C restatement of Fast_MPC/VAR_1 as written (oracle/fmpc_ref_general.c)",
+                                       "steps_per_s": 1 / dt2, "cores": 1, "sample": f"{nst2} closed-loop steps, one instance"}}), flush=True)
 
 
 def bench_c5(nb=int(os.environ.get("C5_NB", "2048"))):
