@@ -711,17 +711,19 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                         while (task >= (rt + 1) * (rt + 2) / 2) ++rt;
                         const int ct = task - rt * (rt + 1) / 2;
                         const int r = 8 * rt + gq, cc = 8 * ct + 2 * q;
-                        double i0 = 0.0, i1 = 0.0;
+                        // the four loads are issued here and only consumed after the tile products (no add in between: an
+                        // in-order warp would otherwise wait for L2 before its first DMMA)
+                        double i0 = 0.0, i1 = 0.0, d0 = 0.0, d1 = 0.0;
                         if (r < n) {
-                            if (cc <= r) { i0 = __ldg(Yd + r * n + cc); if (i < T) i0 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc]; }
-                            if (cc + 1 <= r) { i1 = __ldg(Yd + r * n + cc + 1); if (i < T) i1 += Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc + 1]; }
+                            if (cc <= r) { i0 = __ldg(Yd + r * n + cc); if (i < T) d0 = Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc]; }
+                            if (cc + 1 <= r) { i1 = __ldg(Yd + r * n + cc + 1); if (i < T) d1 = Dsc[(size_t)i * Mp + r * (r + 1) / 2 + cc + 1]; }
                         }
                         double p0 = 0.0, p1 = 0.0;
                         if (up1) tile_nt(p0, p1, bL1p + (8 * rt + gq) * ld + q, bL1p + (8 * ct + gq) * ld + q, ks);
                         if (up2) tile_nt(p0, p1, bL2pp + (8 * rt + gq) * ld + q, bL2pp + (8 * ct + gq) * ld + q, ks);
                         if (r < n) {
-                            if (cc <= r) bS[r * lds + cc] = i0 - p0;
-                            if (cc + 1 <= r) bS[r * lds + cc + 1] = i1 - p1;
+                            if (cc <= r) bS[r * lds + cc] = (i0 + d0) - p0;
+                            if (cc + 1 <= r) bS[r * lds + cc + 1] = (i1 + d1) - p1;
                         }
                     } else {
                         const int tk = task - nS, rt = tk / nt, ct = tk - rt * nt;
