@@ -210,6 +210,12 @@ def main():
     from mpc_sensorlessao_b200 import synth
     from mpc_sensorlessao_b200._lib import load_library
 
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner, warnings) is sent to
+    # stderr at the file-descriptor level and the real stdout is restored just before the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -363,7 +369,10 @@ def main():
                                     "sample": f"all {nbs} instances of one step, {reps} repetitions ({reps * dt:.1f} s), structured "
                                               "C/OpenMP port (oracle/fmpc_ref.c) on every host thread; the MATLAB reference cannot "
                                               "run on this box"}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     hb.close()
     if world > 1:
         dist.destroy_process_group()
