@@ -30,11 +30,12 @@ struct MT19937 {
     }
     uint32_t next32()
     {
-        if (idx >= 624) {
-            for (int i = 0; i < 624; ++i) {
-                uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
-                mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
+        if (idx >= 624) {       // twist, in three modulo-free segments (the closed loop draws millions of values per step)
+            auto tw = [](uint32_t a, uint32_t b) { const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu); return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); };
+            int i = 0;
+            for (; i < 624 - 397; ++i) mt[i] = mt[i + 397] ^ tw(mt[i], mt[i + 1]);
+            for (; i < 623; ++i) mt[i] = mt[i + 397 - 624] ^ tw(mt[i], mt[i + 1]);
+            mt[623] = mt[396] ^ tw(mt[623], mt[0]);
             idx = 0;
         }
         uint32_t y = mt[idx++];

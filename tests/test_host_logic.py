@@ -108,3 +108,22 @@ def test_side_entry_points_validate_before_cuda(pk):
     with pytest.raises(pk.FmpcError) as e:
         pk.identify_var(np.zeros((600, 45)), 2)           # accumulators exceed the kernel's budget
     assert e.value.code == -2
+
+
+def test_library_mt19937_is_matlabs_default_stream(tmp_path):
+    """The library's own generator (nu0 = NULL => rand(length(b),1), inf_newton_solver.m:2) is compiled out of
+    csrc/fmpc_api.cu on the host and compared with MT19937(5489) 53-bit doubles = MATLAB's default stream."""
+    import subprocess
+    src = open(os.path.join(ROOT, "mpc-sensorlessao_b200", "csrc", "fmpc_api.cu")).read()
+    a = src.index("struct MT19937 {")
+    b = src.index("#define CU_OK", a)
+    code = ("#include <cstdint>\n#include <cstdio>\n" + src[a:b] +
+            "\nint main(){ MT19937 g; for (int i = 0; i < 4000; ++i) printf(\"%.17g\\n\", g.rand53()); return 0; }\n")
+    cpp, exe = tmp_path / "mt.cpp", tmp_path / "mt"
+    cpp.write_text(code)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-o", str(exe), str(cpp)])
+    out = np.array([float(x) for x in subprocess.check_output([str(exe)]).split()])
+    ref = np.random.RandomState(5489).random_sample(4000)
+    assert np.array_equal(out, ref)
+    assert abs(out[0] - 0.8147236863931789) < 1e-16 and abs(out[1] - 0.9057919370756192) < 1e-16       # MATLAB: rand after start-up
