@@ -64,11 +64,42 @@ def cpu_port_rate(p, sets, nsample, nthreads=0, reps=1):
     return nb / dt, int(out["iters"].sum()), nb, dt
 
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)      # before any NUMA binding of this rank
+except AttributeError:
+    ORIG_AFFINITY = None
+
+
 def host_threads():
+    return len(ORIG_AFFINITY) if ORIG_AFFINITY else (os.cpu_count() or 1)
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e path are
+    allocated on the GPU's own NUMA node (with several ranks per host the copies otherwise cross the socket interconnect).
+    Returns the number of CPUs bound to, or None if NVML / affinity is unavailable."""
     try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        h = None
+        for i in range(nv.nvmlDeviceGetCount()):
+            hh = nv.nvmlDeviceGetHandleByIndex(i)
+            if nv.nvmlDeviceGetPciInfo(hh).bus == bus:
+                h = hh
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -218,6 +249,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation: first touch decides where the pages live
     if world > 1:
         # NCCL prints its version banner to STDOUT when NCCL_DEBUG is VERSION/WARN: keep stdout to the one JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
@@ -348,7 +380,7 @@ def main():
             "data": "synthetic", "config": workload_desc(),
             "clocks": clocks,
             "e2e": {"value": solves / e2e_s_max, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "fmpc_step (C-ABI, pinned host buffers)"},
+                    "api": "fmpc_step (C-ABI, pinned host buffers)", "numa_bound_cpus": numa},
             "gpu_launches": launches_all,
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA)",
                          "kernel": kname, "achieved": achieved, "peak": peak,
@@ -360,6 +392,8 @@ def main():
             "aggregate_tflops": newton_iters_all * F / (total_ms_max * 1e-3) / 1e12,
         }
         if world == 1 and not args.no_cpu_baseline:
+            if ORIG_AFFINITY:
+                os.sched_setaffinity(0, ORIG_AFFINITY)      # the CPU baseline uses every host thread again
             cores = host_threads()
             nsample = nb
             r0, _, _, dt0 = cpu_port_rate(p, sets, nsample, nthreads=cores, reps=1)
