@@ -4,6 +4,8 @@ with A_s (npix x nmodes, piston column already removed, README.md:289-290) and b
 lsqminnorm is MATLAB's minimum-norm least-squares solve (complete orthogonal decomposition); for the
 full-rank 27 x 27 Gram matrix of the reference model (cond(A_s) = 9.29) it is the unique solution, restated
 here literally (Gram matrix, then numpy's minimum-norm lstsq) and, as a cross-check, through pinv(A_s).
+PARITY UNPINNED by the reference (MATLAB, no golden vectors, cannot run here): pinned on the reference's own DATA
+(model_approx.mat, checksums of SURVEY.md 8c) and by the agreement of the two routes below (tests/test_oracle_estimator.py).
 Only tests/, bench.py's baseline leg and __graft_entry__.smoke() may import this module."""
 import numpy as np
 

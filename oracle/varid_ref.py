@@ -8,6 +8,8 @@ README.md:116-130:
     PARA = (AA'*AA)\\AA'*BB;          % MATLAB precedence: ((AA'*AA)\\AA') * BB
     A1 = (PARA(1:n, :))';  A2 = (PARA(1+n : 2n, :))';
 
+PARITY UNPINNED by the reference (MATLAB, no golden vectors, cannot run here): pinned by recovery of a known model and
+agreement with the benchmark generator's own identification (tests/test_oracle_varid.py).
 Only tests/, bench.py's baseline leg and __graft_entry__.smoke() may import this module."""
 import numpy as np
 
