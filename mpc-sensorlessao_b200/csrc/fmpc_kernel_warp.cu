@@ -303,12 +303,12 @@ __device__ __forceinline__ void stream_issue(const WCtx &c, const StreamIdx<CW> 
 template <int KIND> struct UArr { static constexpr int N = (KIND == K_RP) ? 1 : ((KIND == K_NEWTON || KIND == K_NORM) ? 2 : 5); };
 
 template <int NPOT, int KIND>
-__device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &ss_d, double &ss_p)
+__device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &ss_d, double &ss_p, double &ss_f)
 {
     constexpr int CT = (NPOT + 7) / 8, KS = NPOT / 4, LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4, NA = UArr<KIND>::N, npad = 8 * CT;
     constexpr int XU = 4;
     const int n = c.n, m = c.m, T = c.T, mpad = c.mpad, gq = c.gq, q = c.q, lane = c.lane;
-    ss_d = 0.0; ss_p = 0.0;
+    ss_d = 0.0; ss_p = 0.0; ss_f = 0.0;
     // the u-space streams of this pass were written long ago (they have left L2 for DRAM): pull them back into L2 now,
     // the register pipeline below then only has to cover L2 latency
     {
@@ -364,6 +364,10 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
         }
     }
     __syncwarp();
+    // K_TRIAL also returns ss_f: the dual residual the NEXT iteration's K_NEWTON pass would find at this trial point (barrier
+    // gradient re-evaluated there; same expressions, same summation order, so the sums are bit-identical).  If the trial is
+    // accepted, the early-exit test of the next iteration (inf_newton_solver.m:19-22) is decided without another pass.
+    if (KIND == K_TRIAL) ss_f = ss_d;
     const double *xsrc = (KIND == K_RP) ? c.XC() : (KIND == K_NEWTON ? c.DX() : c.XT());
     // operand row pointers (no predicates: see the conventions above WGeom)
     const double *pB[CT];
@@ -486,6 +490,13 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
                             const double r = rdu_expr(r2, rl, uv, hv, v[h][tt][NA > 4 ? 4 : 0]);
                             const double rm = tok[tt] ? r : 0.0;
                             ss_d = fma(rm, rm, ss_d);
+                            {   // the same element with the barrier gradient of the trial point (what K_NEWTON computes next)
+                                const double sp = pUmax[j4] - uv, sm = uv - pUmin[j4];
+                                const double dp = rcp_nr(sp), dm = rcp_nr(sm);
+                                const double rf = rdu_expr(r2, rl, uv, hv, c.kappa * (dp - dm));
+                                const double rfm = tok[tt] ? rf : 0.0;
+                                ss_f = fma(rfm, rfm, ss_f);
+                            }
                             a[tt] = uv;
                         }
                     }
@@ -1328,26 +1339,17 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
             }
         }
         __syncwarp();
-        double ssd, ssp;
-        pass_Cv<NPOT, K_RP>(c, 0.0, ssd, ssp);                         // z <- start ; r_p = C z - b
+        double ssd, ssp, ssf;
+        pass_Cv<NPOT, K_RP>(c, 0.0, ssd, ssp, ssf);                         // z <- start ; r_p = C z - b
         pass_Ct<NPOT, 0>(c);                                           // images of the dual start nu
         __syncwarp();
         PROF_T(0);
 
         int status = ST_OK, iters = 0;
-        bool likely_exit = false;              // the accepted trial point already met the tolerances with the frozen barrier gradient
+        int next_exit = 0;                     // decided by the accepted trial pass: 1 = early exit, 2 = non-finite residual
         for (int it = 0; it < A.niters; ++it) {
-            if (likely_exit) {
-                // norms only (bit-identical sums): in the closed-loop regime the test passes here and the GEMM of a full pass
-                // would be thrown away; if it does not pass, the full pass below recomputes the same numbers
-                pass_Cv<NPOT, K_NORM>(c, 0.0, ssd, ssp);
-                const double tp0 = warp_sum(ssp), td0 = warp_sum(ssd);
-                const double nrn = sqrt(td0 + tp0);
-                if (!isfinite(nrn)) { status = ST_NONFINITE; break; }
-                if (nrn <= A.tol_r && sqrt(tp0) <= A.tol_p) { status = ST_EARLY_EXIT; break; }
-                __syncwarp();
-            }
-            pass_Cv<NPOT, K_NEWTON>(c, 0.0, ssd, ssp);
+            if (next_exit) { status = (next_exit == 1) ? ST_EARLY_EXIT : ST_NONFINITE; break; }
+            pass_Cv<NPOT, K_NEWTON>(c, 0.0, ssd, ssp, ssf);
             const double tot_p = warp_sum(ssp), tot_d = warp_sum(ssd);
             const double nr0 = sqrt(tot_d + tot_p);
             PROF_T(1);
@@ -1367,11 +1369,14 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
             double t = 1.0;
             int nh = 0;
             for (;;) {
-                pass_Cv<NPOT, K_TRIAL>(c, t, ssd, ssp);
+                pass_Cv<NPOT, K_TRIAL>(c, t, ssd, ssp, ssf);
                 const double tp = warp_sum(ssp), td = warp_sum(ssd);
                 const double nrt = sqrt(td + tp);
                 __syncwarp();
-                likely_exit = (nrt <= 4.0 * A.tol_r) && (sqrt(tp) <= 4.0 * A.tol_p);
+                {   // residual of the next iteration at this trial point (valid if this trial is the accepted one)
+                    const double nrn = sqrt(warp_sum(ssf) + tp);
+                    next_exit = !isfinite(nrn) ? 2 : ((nrn <= A.tol_r && sqrt(tp) <= A.tol_p) ? 1 : 0);
+                }
                 if (!(nrt > (1.0 - A.alpha * t) * nr0)) break;
                 if (t == 0.0) break;
                 if (A.ls_max > 0 && nh >= A.ls_max) { status = ST_LS_MAX; break; }
