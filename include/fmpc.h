@@ -46,7 +46,7 @@ enum {
     FMPC_ERR_B_SIZE         = -11,  /* fast_mpc_eq_const.m:31-32   'The equality control dynamics matrix size does not match' */
     FMPC_ERR_INIT_SIZE      = -12,  /* fast_mpc_init.m:13-14       'Initialization size mismatch (T*(n+m))' */
     FMPC_ERR_NOT_PD         = -13,  /* chol() failure on a problem-constant block (Q, Qf, R) */
-    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover (non-diagonal R) */
+    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover (non-diagonal R, n > 72) */
     FMPC_ERR_BATCH          = -15,  /* nbatch > max_batch of the handle */
     FMPC_ERR_CUDA           = -16,  /* no usable sm_100 device / CUDA runtime error (no CPU fallback) */
     FMPC_ERR_PARAM          = -17   /* kappa <= 0, niters < 0, beta not in (0,1) ... */
@@ -193,7 +193,7 @@ long long fmpc_launch_count(const fmpc_handle *h);
  * requires a device sync, so call it outside timed regions. */
 long long fmpc_last_newton_iters(fmpc_handle *h);
 /* Which solve kernel the handle selected: 2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA-per-instance
- * DMMA kernel (32 < n <= 72), 0 = generic kernel (n > 72), 3 = general-structure kernel (VAR_1 ramp rows, literal
+ * DMMA kernel (32 < n <= 72), 0 = scalar reference kernel (only when forced), 3 = general-structure kernel (VAR_1 ramp rows, literal
  * VAR_1 columns, dense Q / Qf). */
 int fmpc_kernel_kind(const fmpc_handle *h);
 /* Phase cycle counters of the last solve launch, summed over warps (all zero unless the library was
