@@ -239,8 +239,9 @@ struct WCtx {
     __device__ __forceinline__ double *gL2() const { return fa(2); }
 };
 
-// K_NORM: the residual norms of K_NEWTON (same expressions, same summation order) without its GEMM and scratch stores --
-// the early-exit test of an iteration that is expected to pass it (inf_newton_solver.m:19-22)
+// K_NORM: the residual norms of K_NEWTON (same expressions, same summation order) without its GEMM and scratch stores.
+// Not instantiated at present: the accepted K_TRIAL pass now returns the next iteration's residual itself (ss_f), which
+// made the separate norm-only pass of v3.8 unnecessary; the variant is kept for callers that need the norms alone.
 enum { K_RP = 0, K_NEWTON = 1, K_TRIAL = 2, K_NORM = 3 };
 
 // ---------------------------------------------------------------------------------------------
