@@ -140,6 +140,32 @@ int fmpc_step_d(fmpc_handle *h, const fmpc_params *p, int nbatch,
                 const double *X0, const double *U0, const double *nu0,
                 double *X, double *U, int *status, int *iters, void *stream);
 
+/* Resident closed-loop step: what the loop body of README.md:444-626 needs from the solver and nothing more.  The handle
+ * keeps the solution (X, U) of its previous fmpc_step_r call on the device and warm-starts from it shifted one stage
+ * (stage t <- t + 1, last stage repeated); it also keeps the previous x0 (= x0_pre of this step, README.md:483-488) and the
+ * input it returned last (= u_prev of the VAR_1 ramp rows, README.md:447-452).  Per step the caller sends the estimator
+ * output x0 and receives the input the loop applies, U(:,0) (README.md:589); nothing of the horizon crosses the host
+ * link unless X / U are requested.  HOST buffers, blocking.
+ *   flags   FMPC_R_RESET: first step of a loop -- cold start (fast_mpc_init.m:19-25), x0_pre = 0, u_prev = 0
+ *           (README.md:483-485, 446-448).  Required on the first call and whenever nbatch changes.
+ *   x0_pre  NULL => x0 of the previous call on this handle        u_prev  NULL => U(:,0) of the previous call (ramp rows only)
+ *   w, xf   as in fmpc_step (NULL = zeros / no terminal row)       nu0  NULL => the handle's MATLAB stream, as in fmpc_step
+ *   u0      m x nb  output: U(:,0) per instance
+ *   X, U    both NULL, or full horizons as in fmpc_step (n x T x nb, m x T x nb)
+ * Equals fmpc_step called with X0 / U0 = the previous outputs shifted one stage (tests/test_gpu_fmpc.py). */
+enum { FMPC_R_RESET = 1 };
+int fmpc_step_r(fmpc_handle *h, const fmpc_params *p, int nbatch, int flags,
+                const double *x0, const double *x0_pre, const double *u_prev,
+                const double *w, const double *xf, const double *nu0,
+                double *u0, double *X, double *U, int *status, int *iters, double *telapsed);
+
+/* The same step on DEVICE buffers, asynchronous on `stream` (NULL = the handle's own stream): for drivers that keep the
+ * estimator output and the applied input on the GPU too.  Calls on one handle must be issued in order on one stream. */
+int fmpc_step_r_d(fmpc_handle *h, const fmpc_params *p, int nbatch, int flags,
+                  const double *x0, const double *x0_pre, const double *u_prev,
+                  const double *w, const double *xf, const double *nu0,
+                  double *u0, double *X, double *U, int *status, int *iters, void *stream);
+
 /* Interleaved convenience wrapper with the reference's own I/O shape: z0 / z are
  * (T (n+m)) x nb in the layout of fast_mpc_init.m:22-25; z0 NULL => cold start. */
 int fmpc_step_z(fmpc_handle *h, const fmpc_params *p, int nbatch,

@@ -42,7 +42,7 @@ class FmpcParams(C.Structure):
 # every symbol include/fmpc.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "fmpc_default_params", "fmpc_device_count", "fmpc_create", "fmpc_destroy", "fmpc_step", "fmpc_step_d",
-    "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
+    "fmpc_step_r", "fmpc_step_r_d", "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
     "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
@@ -86,6 +86,8 @@ def load_library():
     step_args = [vp, C.POINTER(FmpcParams), C.c_int] + [vp] * 10 + [vp, vp]
     L.fmpc_step.argtypes = step_args + [vp]                # ..., status, iters, telapsed
     L.fmpc_step_d.argtypes = step_args + [vp]              # ..., status, iters, stream
+    L.fmpc_step_r.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6 + [vp] * 6
+    L.fmpc_step_r_d.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6 + [vp] * 6
     L.fmpc_step_z.argtypes = [vp, C.POINTER(FmpcParams), C.c_int] + [vp] * 8 + [vp, vp, vp]
     L.fmpc_frontend.argtypes = [vp, C.c_int, C.POINTER(FmpcParams), C.c_double, C.c_double, C.c_int] + [vp] * 10 + [vp, vp, vp]
     L.fmpc_frontend_nouter.argtypes = [vp, C.c_int]

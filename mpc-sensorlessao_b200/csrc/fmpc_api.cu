@@ -7,7 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <utility>
 #include <vector>
 #include "../../include/fmpc.h"
 #include "fmpc_internal.h"
@@ -16,7 +20,8 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------
 // MATLAB's default global stream: MT19937 seeded with 5489, doubles from genrand_res53
-// (`rand` in inf_newton_solver.m:2).
+// (`rand` in inf_newton_solver.m:2).  The host only seeds the state; the stream itself is
+// generated on the device (fmpc_mt_fill_kernel).
 // ---------------------------------------------------------------------------------------------
 struct MT19937 {
     uint32_t mt[624];
@@ -27,25 +32,6 @@ struct MT19937 {
         mt[0] = seed;
         for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
         idx = 624;
-    }
-    uint32_t next32()
-    {
-        if (idx >= 624) {       // twist, in three modulo-free segments (the closed loop draws millions of values per step)
-            auto tw = [](uint32_t a, uint32_t b) { const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu); return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu); };
-            int i = 0;
-            for (; i < 624 - 397; ++i) mt[i] = mt[i + 397] ^ tw(mt[i], mt[i + 1]);
-            for (; i < 623; ++i) mt[i] = mt[i + 397 - 624] ^ tw(mt[i], mt[i + 1]);
-            mt[623] = mt[396] ^ tw(mt[623], mt[0]);
-            idx = 0;
-        }
-        uint32_t y = mt[idx++];
-        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-        return y;
-    }
-    double rand53()
-    {
-        const uint32_t a = next32() >> 5, b = next32() >> 6;
-        return (a * 67108864.0 + b) / 9007199254740992.0;
     }
 };
 
@@ -67,6 +53,89 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     template <class T> T *as() const { return (T *)p; }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Pageable host buffers (what mxGetPr hands the MEX gateway): cudaMemcpyAsync from / to them is a synchronous staged
+// copy inside the driver, which serialises the copy-in / solve / copy-out pipeline of fmpc_step.  Instead the library stages
+// them itself: a few worker threads memcpy each chunk between the caller's buffer and a ring of pinned slots, and the DMA
+// engines only ever see pinned memory.
+// ---------------------------------------------------------------------------------------------
+struct CopyPool {
+    struct Job { char *dst; const char *src; size_t bytes; };
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<Job> jobs;
+    size_t next = 0, pending = 0;
+    bool stop = false;
+    void start(int nthreads)
+    {
+        for (int i = 0; i < nthreads; ++i) th.emplace_back([this] { run(); });
+    }
+    void run()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [this] { return stop || next < jobs.size(); });
+            if (stop) return;
+            const Job j = jobs[next++];
+            lk.unlock();
+            std::memcpy(j.dst, j.src, j.bytes);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+    // copies every (dst, src, bytes) triple, cut into pieces of <= 1 MiB, on the workers and the calling thread
+    void copy(const std::vector<Job> &list)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        jobs.clear(); next = 0;
+        const size_t piece = (size_t)1 << 20;
+        for (const Job &j : list)
+            for (size_t o = 0; o < j.bytes; o += piece) jobs.push_back({j.dst + o, j.src + o, (j.bytes - o < piece) ? j.bytes - o : piece});
+        pending = jobs.size();
+        if (!pending) return;
+        cv_work.notify_all();
+        while (next < jobs.size()) {          // the caller works too
+            const Job j = jobs[next++];
+            lk.unlock();
+            std::memcpy(j.dst, j.src, j.bytes);
+            lk.lock();
+            --pending;
+        }
+        cv_done.wait(lk, [this] { return pending == 0; });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : th) t.join();
+    }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        if (cudaMallocHost(&p, need) != cudaSuccess) return -1;
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
+// true if the DMA engines can reach `p` directly (pinned / registered host memory, device or managed memory)
+bool dma_reachable(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type != cudaMemoryTypeUnregistered;
+}
 
 bool is_diag(const double *A, int n)
 {
@@ -100,10 +169,24 @@ struct fmpc_handle {
     DevBuf d_x0, d_x0pre, d_uprev, d_w, d_xf, d_X, d_U, d_nu0, d_status, d_iters;
     // closed-loop state
     DevBuf d_a, d_Uacc, d_Xacc, d_itacc;
-    MT19937 rng;
     long long launches = 0;
     size_t ws_stride = 0;
-    std::vector<double> h_nu;             // host staging for generated nu0
+    // MATLAB's default stream on the device (nu0 == NULL): MT19937 state (624 words + read index) and two buffers of stream
+    // doubles.  nu_buf[nu_cur][0 .. nu_have) are the next unread doubles, generated on s_gen ahead of the call that uses them.
+    DevBuf d_mt, nu_buf[2];
+    int nu_cur = 0;
+    size_t nu_have = 0, nu_cap = 0;
+    cudaStream_t s_gen = nullptr;
+    cudaEvent_t ev_nu_ready[2] = {}, ev_nu_free[2] = {};
+    bool nu_free_pending[2] = {false, false};
+    // staging of pageable host buffers (fmpc_step): NSTAGE pinned slots per direction, worker threads created on first use
+    static constexpr int NSTAGE = 3;
+    PinBuf stg_in[NSTAGE], stg_out[NSTAGE];
+    cudaEvent_t ev_stg_in[NSTAGE] = {}, ev_stg_out[NSTAGE] = {};
+    CopyPool *pool = nullptr;
+    // resident closed-loop state of fmpc_step_r: the previous solution (r_X, r_U), x0 of the previous call, U(:,0)
+    DevBuf r_X, r_U, r_x0, r_x0pre, r_u0;
+    int r_nb = 0;                         // instances the resident state is valid for (0 = none: the next call must reset)
 };
 
 namespace {
@@ -282,8 +365,17 @@ void fmpc_destroy(fmpc_handle *h)
     cudaSetDevice(h->device);
     for (void *p : h->sys_allocs) cudaFree(p);
     DevBuf *bufs[] = {&h->ws, &h->counters, &h->d_x0, &h->d_x0pre, &h->d_uprev, &h->d_w, &h->d_xf, &h->d_X, &h->d_U,
-                      &h->d_nu0, &h->d_status, &h->d_iters, &h->d_a, &h->d_Uacc, &h->d_Xacc, &h->d_itacc};
+                      &h->d_nu0, &h->d_status, &h->d_iters, &h->d_a, &h->d_Uacc, &h->d_Xacc, &h->d_itacc,
+                      &h->d_mt, &h->nu_buf[0], &h->nu_buf[1], &h->r_X, &h->r_U, &h->r_x0, &h->r_x0pre, &h->r_u0};
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) { if (h->ev_nu_ready[i]) cudaEventDestroy(h->ev_nu_ready[i]); if (h->ev_nu_free[i]) cudaEventDestroy(h->ev_nu_free[i]); }
+    if (h->s_gen) cudaStreamDestroy(h->s_gen);
+    for (int i = 0; i < fmpc_handle::NSTAGE; ++i) {
+        h->stg_in[i].release(); h->stg_out[i].release();
+        if (h->ev_stg_in[i]) cudaEventDestroy(h->ev_stg_in[i]);
+        if (h->ev_stg_out[i]) cudaEventDestroy(h->ev_stg_out[i]);
+    }
+    delete h->pool;
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     for (int i = 0; i < fmpc_handle::MAX_CHUNKS; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]); }
@@ -406,6 +498,20 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     for (int i = 0; ok && i < fmpc_handle::MAX_CHUNKS; ++i)
         if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (ok && cudaStreamCreateWithFlags(&h->s_gen, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    for (int i = 0; ok && i < 2; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_nu_ready[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_nu_free[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
+    for (int i = 0; ok && i < fmpc_handle::NSTAGE; ++i)
+        if (cudaEventCreateWithFlags(&h->ev_stg_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_stg_out[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
+    if (ok) {   // rand's generator as a fresh MATLAB session has it: MT19937 seeded with 5489, nothing drawn yet
+        MT19937 g(5489u);
+        uint32_t st[625];
+        std::memcpy(st, g.mt, sizeof(g.mt));
+        st[624] = 624u;
+        if (h->d_mt.ensure(sizeof(st)) || cudaMemcpy(h->d_mt.p, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    }
     if (!ok) { fmpc_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
     return FMPC_OK;
@@ -450,12 +556,59 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
     return (long long)v;
 }
 
+// The next `need` doubles of the handle's MATLAB stream, in device memory, readable by work enqueued on `consumer` after this
+// call.  The doubles for the FOLLOWING call (assumed to need as many) are generated right away on s_gen into the other buffer,
+// underneath the solve that consumes this one; whatever a call leaves unread is carried over, so the stream is consumed
+// strictly in order whatever the batch sizes.  The consumer calls nu_release(which) once its last reader is enqueued.
+static int nu_take(fmpc_handle *h, size_t need, cudaStream_t consumer, const double **ptr, int *which)
+{
+    const size_t cap = (size_t)h->max_batch * (size_t)(h->T + 1) * (size_t)h->n;
+    if (need > cap) return FMPC_ERR_BATCH;
+    if (h->nu_cap < cap) {
+        if (h->nu_buf[0].ensure(cap * 8) || h->nu_buf[1].ensure(cap * 8)) return FMPC_ERR_CUDA;
+        h->nu_cap = cap;
+    }
+    const int cur = h->nu_cur, oth = cur ^ 1;
+    double *B = h->nu_buf[cur].as<double>(), *O = h->nu_buf[oth].as<double>();
+    if (h->nu_have < need) {
+        if (h->nu_free_pending[cur]) { CU_OK(cudaStreamWaitEvent(h->s_gen, h->ev_nu_free[cur], 0)); h->nu_free_pending[cur] = false; }
+        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), B + h->nu_have, need - h->nu_have, h->s_gen);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+        h->nu_have = need;
+    }
+    CU_OK(cudaEventRecord(h->ev_nu_ready[cur], h->s_gen));
+    CU_OK(cudaStreamWaitEvent(consumer, h->ev_nu_ready[cur], 0));
+    *ptr = B;
+    *which = cur;
+    const size_t left = h->nu_have - need;
+    if (h->nu_free_pending[oth]) { CU_OK(cudaStreamWaitEvent(h->s_gen, h->ev_nu_free[oth], 0)); h->nu_free_pending[oth] = false; }
+    if (left) CU_OK(cudaMemcpyAsync(O, B + need, left * 8, cudaMemcpyDeviceToDevice, h->s_gen));
+    size_t have = left;
+    if (left < need) {
+        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), O + left, need - left, h->s_gen);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+        have = need;
+    }
+    h->nu_cur = oth;
+    h->nu_have = have;
+    return FMPC_OK;
+}
+static int nu_release(fmpc_handle *h, int which, cudaStream_t consumer)
+{
+    CU_OK(cudaEventRecord(h->ev_nu_free[which], consumer));
+    h->nu_free_pending[which] = true;
+    return FMPC_OK;
+}
+
 static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
                        const double *u_prev, const double *w, const double *xf, const double *X0, const double *U0, const double *nu0,
                        double *X, double *U, int *status, int *iters, cudaStream_t st, bool keep_totals = false,
-                       int part = 0, int nparts = 1, bool by_smid = false)
+                       int part = 0, int nparts = 1, bool by_smid = false, int warm_shift = 0, double *u_first = nullptr)
 {
     StepArgs A{};
+    A.warm_shift = warm_shift; A.u_first = u_first;
     A.nbatch = nbatch; A.has_xf = xf ? 1 : 0; A.cold = (X0 == nullptr || U0 == nullptr) ? 1 : 0;
     A.kappa = p->kappa; A.niters = p->niters; A.ls_max = p->ls_max;
     A.alpha = p->alpha; A.beta = p->beta; A.tol_r = p->tol_r; A.tol_p = p->tol_p;
@@ -526,12 +679,9 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
         h->d_uprev.ensure(nb * m * 8) || h->d_X.ensure(nb * n * T * 8) || h->d_U.ensure(nb * m * T * 8) || h->d_nu0.ensure(nb * NBn * 8) ||
         h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4))
         return FMPC_ERR_CUDA;
-    const double *nu_src = nu0;
-    if (!nu0) {     // MATLAB default stream, one rand(length(b),1) per instance, instance after instance
-        h->h_nu.resize(nb * NBn);
-        for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
-        nu_src = h->h_nu.data();
-    }
+    // nu0 == NULL: MATLAB default stream, one rand(length(b),1) per instance, instance after instance -- generated on the device
+    const double *nu_dev = nullptr;
+    int nu_which = -1;
     // Instances are independent: the batch is cut into chunks, and copy-in (s_in), solve and copy-out (s_out) of successive
     // chunks overlap.  The warp kernel additionally splits the SMs (and its per-slot scratch) into NP partitions, each with its
     // own solve stream: chunk c runs as one wave on partition c % NP, so NP chunk kernels are resident side by side and the
@@ -560,31 +710,72 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     const size_t Tn = (size_t)T * n, Tm = (size_t)T * m;
     while (nch > 1 && (size_t)(nch - 1) * per >= nb) --nch;           // no empty trailing chunk
     if (smid_mode) CU_OK(cudaMemsetAsync(h->counters.p, 0, 256 * fmpc_handle::MAX_CHUNKS, si));   // every chunk's counter block, ahead of all chunks
+    if (!nu0) { rc = nu_take(h, nb * NBn, si, &nu_dev, &nu_which); if (rc) return rc; }
     // the per-instance vectors are small: one copy each for the whole batch, ahead of the chunked arrays
     CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, si));
     if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, si));
     if (u_prev && h->ramp) CU_OK(cudaMemcpyAsync(h->d_uprev.p, u_prev, nb * m * 8, cudaMemcpyHostToDevice, si));
     if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.p, xf, nb * n * 8, cudaMemcpyHostToDevice, si));
-    // enqueue order per chunk: copy-in(ci), solve(ci), copy-out(ci-1) -- so that even blocking (pageable) copies
-    // leave the solve of the current chunk running underneath them
+    // pageable caller buffers go through the pinned staging ring (see CopyPool); pinned / registered ones are copied directly
+    const bool stage_in = !(dma_reachable(w) && dma_reachable(X0) && dma_reachable(U0) && dma_reachable(nu0));
+    const bool stage_out = !(dma_reachable(X) && dma_reachable(U));
+    constexpr int NSTG = fmpc_handle::NSTAGE;
+    if (stage_in || stage_out) {
+        if (!h->pool) {
+            h->pool = new (std::nothrow) CopyPool();
+            if (!h->pool) return FMPC_ERR_CUDA;
+            int nt = (int)std::thread::hardware_concurrency() - 1;
+            if (const char *e = getenv("FMPC_COPY_THREADS")) nt = atoi(e);
+            h->pool->start(nt < 0 ? 0 : (nt > 7 ? 7 : nt));
+        }
+        const size_t in_b = per * ((w ? Tn : 0) + (X0 ? Tn + Tm : 0) + (nu0 ? NBn : 0)) * 8, out_b = per * (Tn + Tm) * 8;
+        for (int i = 0; i < NSTG; ++i)
+            if ((stage_in && h->stg_in[i].ensure(in_b)) || (stage_out && h->stg_out[i].ensure(out_b))) return FMPC_ERR_CUDA;
+    }
+    auto drain = [&](int cj) -> int {         // chunk cj: pinned out-slot -> the caller's X, U
+        const size_t b0 = (size_t)cj * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
+        CU_OK(cudaEventSynchronize(h->ev_stg_out[cj % NSTG]));
+        char *sp = (char *)h->stg_out[cj % NSTG].p;
+        h->pool->copy({{(char *)(X + b0 * Tn), sp, cb * Tn * 8}, {(char *)(U + b0 * Tm), sp + cb * Tn * 8, cb * Tm * 8}});
+        return FMPC_OK;
+    };
+    // enqueue order per chunk: copy-in(ci), solve(ci), copy-out(ci-1) -- the host-side staging copies of one chunk run
+    // underneath the solve of the previous one
     for (int ci = 0; ci <= nch; ++ci) {
         if (ci < nch) {
             const size_t b0 = (size_t)ci * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
             const int part = smid_mode ? ci : ci % NP;
             cudaStream_t sk = smid_mode ? h->s_k[ci % fmpc_handle::MAX_PART] : ((NP > 1) ? h->s_k[part] : st);
-            if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, w + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
-            if (X0) {
-                CU_OK(cudaMemcpyAsync(h->d_X.as<double>() + b0 * Tn, X0 + b0 * Tn, cb * Tn * 8, cudaMemcpyHostToDevice, si));
-                CU_OK(cudaMemcpyAsync(h->d_U.as<double>() + b0 * Tm, U0 + b0 * Tm, cb * Tm * 8, cudaMemcpyHostToDevice, si));
+            const double *sw = w ? w + b0 * Tn : nullptr, *sX0 = X0 ? X0 + b0 * Tn : nullptr, *sU0 = U0 ? U0 + b0 * Tm : nullptr,
+                         *snu = nu0 ? nu0 + b0 * NBn : nullptr;
+            if (stage_in) {
+                const int slot = ci % NSTG;
+                if (ci >= NSTG) CU_OK(cudaEventSynchronize(h->ev_stg_in[slot]));      // its previous DMA is done
+                char *sp = (char *)h->stg_in[slot].p;
+                std::vector<CopyPool::Job> jobs;
+                auto put = [&](const double *&src, size_t bytes) {
+                    if (!src) return;
+                    jobs.push_back({sp, (const char *)src, bytes});
+                    src = (const double *)sp;
+                    sp += bytes;
+                };
+                put(sw, cb * Tn * 8); put(sX0, cb * Tn * 8); put(sU0, cb * Tm * 8); put(snu, cb * NBn * 8);
+                h->pool->copy(jobs);
             }
-            CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + b0 * NBn, nu_src + b0 * NBn, cb * NBn * 8, cudaMemcpyHostToDevice, si));
+            if (w) CU_OK(cudaMemcpyAsync(h->d_w.as<double>() + b0 * Tn, sw, cb * Tn * 8, cudaMemcpyHostToDevice, si));
+            if (X0) {
+                CU_OK(cudaMemcpyAsync(h->d_X.as<double>() + b0 * Tn, sX0, cb * Tn * 8, cudaMemcpyHostToDevice, si));
+                CU_OK(cudaMemcpyAsync(h->d_U.as<double>() + b0 * Tm, sU0, cb * Tm * 8, cudaMemcpyHostToDevice, si));
+            }
+            if (nu0) CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + b0 * NBn, snu, cb * NBn * 8, cudaMemcpyHostToDevice, si));
+            if (stage_in) CU_OK(cudaEventRecord(h->ev_stg_in[ci % NSTG], si));
             CU_OK(cudaEventRecord(h->ev_in[ci], si));
             CU_OK(cudaStreamWaitEvent(sk, h->ev_in[ci], 0));
             if (ci == 0) CU_OK(cudaEventRecord(h->ev0, sk));
             rc = step_device(h, p, (int)cb, h->d_x0.as<double>() + b0 * n, x0_pre ? h->d_x0pre.as<double>() + b0 * n : nullptr,
                              (u_prev && h->ramp) ? h->d_uprev.as<double>() + b0 * m : nullptr, w ? h->d_w.as<double>() + b0 * Tn : nullptr, xf ? h->d_xf.as<double>() + b0 * n : nullptr,
                              X0 ? h->d_X.as<double>() + b0 * Tn : nullptr, X0 ? h->d_U.as<double>() + b0 * Tm : nullptr,
-                             h->d_nu0.as<double>() + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
+                             (nu0 ? h->d_nu0.as<double>() : nu_dev) + b0 * NBn, h->d_X.as<double>() + b0 * Tn, h->d_U.as<double>() + b0 * Tm,
                              h->d_status.as<int>() + b0, h->d_iters.as<int>() + b0, sk, smid_mode ? true : ci >= NP, part, NP, smid_mode);
             if (rc) return rc;
             CU_OK(cudaEventRecord(h->ev_k[ci], sk));
@@ -594,18 +785,132 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
             const int cj = ci - 1;
             const size_t b0 = (size_t)cj * per, b1 = (b0 + per < nb) ? b0 + per : nb, cb = b1 - b0;
             CU_OK(cudaStreamWaitEvent(so, h->ev_k[cj], 0));
-            CU_OK(cudaMemcpyAsync(X + b0 * Tn, h->d_X.as<double>() + b0 * Tn, cb * Tn * 8, cudaMemcpyDeviceToHost, so));
-            CU_OK(cudaMemcpyAsync(U + b0 * Tm, h->d_U.as<double>() + b0 * Tm, cb * Tm * 8, cudaMemcpyDeviceToHost, so));
+            double *dX = X + b0 * Tn, *dU = U + b0 * Tm;
+            if (stage_out) { dX = (double *)h->stg_out[cj % NSTG].p; dU = dX + cb * Tn; }
+            CU_OK(cudaMemcpyAsync(dX, h->d_X.as<double>() + b0 * Tn, cb * Tn * 8, cudaMemcpyDeviceToHost, so));
+            CU_OK(cudaMemcpyAsync(dU, h->d_U.as<double>() + b0 * Tm, cb * Tm * 8, cudaMemcpyDeviceToHost, so));
+            if (stage_out) {
+                CU_OK(cudaEventRecord(h->ev_stg_out[cj % NSTG], so));
+                if (cj >= 1) { rc = drain(cj - 1); if (rc) return rc; }
+            }
         }
     }
+    if (stage_out) { rc = drain(nch - 1); if (rc) return rc; }
     if (status) CU_OK(cudaMemcpyAsync(status, h->d_status.p, nb * 4, cudaMemcpyDeviceToHost, so));
     if (iters) CU_OK(cudaMemcpyAsync(iters, h->d_iters.p, nb * 4, cudaMemcpyDeviceToHost, so));
     CU_OK(cudaEventRecord(h->ev1, st));
+    if (nu_which >= 0) { rc = nu_release(h, nu_which, st); if (rc) return rc; }
     CU_OK(cudaStreamSynchronize(so));
     CU_OK(cudaStreamSynchronize(st));
     CU_OK(cudaStreamSynchronize(si));
     if (telapsed) { float ms = 0.f; CU_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *telapsed = ms * 1e-3; }
     return FMPC_OK;
+}
+
+// Shared body of fmpc_step_r (host buffers, blocking) and fmpc_step_r_d (device buffers, asynchronous on `st`): every copy is
+// cudaMemcpyDefault, so the same code moves host or device operands.
+static int step_resident(fmpc_handle *h, const fmpc_params *p, int nbatch, int flags, const double *x0, const double *x0_pre,
+                         const double *u_prev, const double *w, const double *xf, const double *nu0,
+                         double *u0, double *X, double *U, int *status, int *iters, double *telapsed, cudaStream_t st, bool blocking)
+{
+    if (!h || !x0 || !u0) return FMPC_ERR_NULL;
+    int rc = validate_params(p);
+    if (rc) return rc;
+    if (nbatch < 0) return FMPC_ERR_DIM;
+    if (nbatch > h->max_batch) return FMPC_ERR_BATCH;
+    if ((X == nullptr) != (U == nullptr)) return FMPC_ERR_NULL;
+    const bool reset = (flags & FMPC_R_RESET) != 0;
+    if (!reset && h->r_nb != nbatch) return FMPC_ERR_INIT_SIZE;      // no resident solution of that size to warm-start from
+    if (telapsed) *telapsed = 0.0;
+    if (nbatch == 0) return FMPC_OK;
+    CU_OK(cudaSetDevice(h->device));
+    const int n = h->n, m = h->m, T = h->T;
+    const size_t nb = (size_t)nbatch, Tn = (size_t)T * n, Tm = (size_t)T * m, NBn = (size_t)(T + (xf ? 1 : 0)) * n;
+    if (h->r_X.ensure(nb * Tn * 8) || h->r_U.ensure(nb * Tm * 8) || h->r_x0.ensure(nb * n * 8) || h->r_x0pre.ensure(nb * n * 8) ||
+        h->r_u0.ensure(nb * m * 8) || h->d_status.ensure(nb * 4) || h->d_iters.ensure(nb * 4) ||
+        (w && h->d_w.ensure(nb * Tn * 8)) || (xf && h->d_xf.ensure(nb * n * 8)) || (u_prev && h->d_uprev.ensure(nb * m * 8)) ||
+        (nu0 && h->d_nu0.ensure(nb * NBn * 8)))
+        return FMPC_ERR_CUDA;
+    // x0_pre = the x0 of the previous call (README.md:483-488: zeros at the first step) unless the caller passes one
+    std::swap(h->r_x0, h->r_x0pre);
+    if (reset) {
+        h->r_nb = 0;
+        CU_OK(cudaMemsetAsync(h->r_x0pre.p, 0, nb * n * 8, st));
+        CU_OK(cudaMemsetAsync(h->r_u0.p, 0, nb * m * 8, st));        // u_prev of the first step (README.md:447-452: no ramp shift yet)
+    }
+    CU_OK(cudaMemcpyAsync(h->r_x0.p, x0, nb * n * 8, cudaMemcpyDefault, st));
+    if (x0_pre) CU_OK(cudaMemcpyAsync(h->r_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyDefault, st));
+    const double *d_up = nullptr;
+    if (h->ramp) {       // ramp rows need the input applied last: the caller's, else U(:,0) of the previous call
+        if (u_prev) {
+            CU_OK(cudaMemcpyAsync(h->d_uprev.p, u_prev, nb * m * 8, cudaMemcpyDefault, st));
+            d_up = h->d_uprev.as<double>();
+        } else {
+            if (h->d_uprev.ensure(nb * m * 8)) return FMPC_ERR_CUDA;
+            CU_OK(cudaMemcpyAsync(h->d_uprev.p, h->r_u0.p, nb * m * 8, cudaMemcpyDeviceToDevice, st));
+            d_up = h->d_uprev.as<double>();
+        }
+    }
+    if (w) CU_OK(cudaMemcpyAsync(h->d_w.p, w, nb * Tn * 8, cudaMemcpyDefault, st));
+    if (xf) CU_OK(cudaMemcpyAsync(h->d_xf.p, xf, nb * n * 8, cudaMemcpyDefault, st));
+    const double *nu_dev = nullptr;
+    int nu_which = -1;
+    if (nu0) {
+        CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu0, nb * NBn * 8, cudaMemcpyDefault, st));
+        nu_dev = h->d_nu0.as<double>();
+    } else {
+        rc = nu_take(h, nb * NBn, st, &nu_dev, &nu_which);
+        if (rc) return rc;
+    }
+    const bool fused = (h->cfg.use_mma == 2);       // the warp kernel reads the shifted warm start and writes U(:,0) itself
+    if (!reset && !fused) {
+        fmpc_launch_shift_inplace(n, m, T, nbatch, h->r_X.as<double>(), h->r_U.as<double>(), st);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+    }
+    if (blocking) CU_OK(cudaEventRecord(h->ev0, st));
+    rc = step_device(h, p, nbatch, h->r_x0.as<double>(), h->var_order == 2 ? h->r_x0pre.as<double>() : nullptr, d_up,
+                     w ? h->d_w.as<double>() : nullptr, xf ? h->d_xf.as<double>() : nullptr,
+                     reset ? nullptr : h->r_X.as<double>(), reset ? nullptr : h->r_U.as<double>(), nu_dev,
+                     h->r_X.as<double>(), h->r_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st,
+                     false, 0, 1, false, (fused && !reset) ? 1 : 0, fused ? h->r_u0.as<double>() : nullptr);
+    if (rc) return rc;
+    if (blocking) CU_OK(cudaEventRecord(h->ev1, st));
+    if (nu_which >= 0) { rc = nu_release(h, nu_which, st); if (rc) return rc; }
+    if (!fused) {
+        fmpc_launch_extract_first(m, T, nbatch, h->r_U.as<double>(), h->r_u0.as<double>(), st);
+        CU_OK(cudaGetLastError());
+        h->launches += 1;
+    }
+    CU_OK(cudaMemcpyAsync(u0, h->r_u0.p, nb * m * 8, cudaMemcpyDefault, st));
+    if (status) CU_OK(cudaMemcpyAsync(status, h->d_status.p, nb * 4, cudaMemcpyDefault, st));
+    if (iters) CU_OK(cudaMemcpyAsync(iters, h->d_iters.p, nb * 4, cudaMemcpyDefault, st));
+    if (X) {
+        CU_OK(cudaMemcpyAsync(X, h->r_X.p, nb * Tn * 8, cudaMemcpyDefault, st));
+        CU_OK(cudaMemcpyAsync(U, h->r_U.p, nb * Tm * 8, cudaMemcpyDefault, st));
+    }
+    h->r_nb = nbatch;
+    if (!blocking) return FMPC_OK;
+    CU_OK(cudaStreamSynchronize(st));
+    if (telapsed) { float ms = 0.f; CU_OK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *telapsed = ms * 1e-3; }
+    return FMPC_OK;
+}
+
+int fmpc_step_r(fmpc_handle *h, const fmpc_params *p, int nbatch, int flags, const double *x0, const double *x0_pre,
+                const double *u_prev, const double *w, const double *xf, const double *nu0,
+                double *u0, double *X, double *U, int *status, int *iters, double *telapsed)
+{
+    if (!h) return FMPC_ERR_NULL;
+    return step_resident(h, p, nbatch, flags, x0, x0_pre, u_prev, w, xf, nu0, u0, X, U, status, iters, telapsed, h->stream, true);
+}
+
+int fmpc_step_r_d(fmpc_handle *h, const fmpc_params *p, int nbatch, int flags, const double *x0, const double *x0_pre,
+                  const double *u_prev, const double *w, const double *xf, const double *nu0,
+                  double *u0, double *X, double *U, int *status, int *iters, void *stream)
+{
+    if (!h) return FMPC_ERR_NULL;
+    return step_resident(h, p, nbatch, flags, x0, x0_pre, u_prev, w, xf, nu0, u0, X, U, status, iters, nullptr,
+                         stream ? (cudaStream_t)stream : h->stream, false);
 }
 
 int fmpc_step_z(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0, const double *x0_pre,
@@ -753,23 +1058,14 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, co
     CU_OK(cudaEventRecord(h->ev0, st));
     // The dual start of step k + 1 is uploaded on the copy stream (two device buffers) while the solve of step k runs: with
     // pageable host memory that copy blocks the calling thread, not the GPU.  ev_in[b]: buffer b filled; ev_k[b]: buffer b consumed.
-    auto upload_nu = [&](int k) -> int {
+    auto upload_nu = [&](int k) -> int {        // explicit dual starts: step k's block goes up while step k - 1 solves
         const int buf = k & 1;
-        const double *nu_src;
-        if (nu0) nu_src = nu0 + (size_t)k * nb * NBn;
-        else {      // MATLAB default stream, one rand(length(b),1) per instance and step
-            h->h_nu.resize(nb * NBn);
-            for (size_t i = 0; i < nb * NBn; ++i) h->h_nu[i] = h->rng.rand53();
-            nu_src = h->h_nu.data();
-        }
         if (k >= 2) CU_OK(cudaStreamWaitEvent(si, h->ev_k[buf], 0));       // the solve of step k - 2 has read this buffer
-        CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + (size_t)buf * nb * NBn, nu_src, nb * NBn * 8, cudaMemcpyHostToDevice, si));
+        CU_OK(cudaMemcpyAsync(h->d_nu0.as<double>() + (size_t)buf * nb * NBn, nu0 + (size_t)k * nb * NBn, nb * NBn * 8, cudaMemcpyHostToDevice, si));
         CU_OK(cudaEventRecord(h->ev_in[buf], si));
-        if (!nu0) CU_OK(cudaStreamSynchronize(si));                        // h_nu is overwritten for the next step
         return FMPC_OK;
     };
-    rc = upload_nu(0);
-    if (rc) return rc;
+    if (nu0) { rc = upload_nu(0); if (rc) return rc; }
     for (int k = 0; k < K; ++k) {
         const int buf = k & 1;
         // x0 = a[:,k,b] + B u_prev ; x0_pre <- previous x0 ; warm start shifted one stage
@@ -778,19 +1074,25 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, co
                                k == 0, st);
         CU_OK(cudaGetLastError());
         h->launches += 1;
-        CU_OK(cudaStreamWaitEvent(st, h->ev_in[buf], 0));
+        const double *nu_k = nullptr;
+        int nu_which = -1;
+        if (nu0) { CU_OK(cudaStreamWaitEvent(st, h->ev_in[buf], 0)); nu_k = h->d_nu0.as<double>() + (size_t)buf * nb * NBn; }
+        else {      // MATLAB default stream, one rand(length(b),1) per instance and step: the device generator runs one step ahead
+            rc = nu_take(h, nb * NBn, st, &nu_k, &nu_which);
+            if (rc) return rc;
+        }
         rc = step_device(h, p, nbatch, h->d_x0.as<double>(), h->d_x0pre.as<double>(), h->d_uprev.as<double>(), nullptr, nullptr,
-                         k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(),
-                         h->d_nu0.as<double>() + (size_t)buf * nb * NBn,
+                         k == 0 ? nullptr : h->d_X.as<double>(), k == 0 ? nullptr : h->d_U.as<double>(), nu_k,
                          h->d_X.as<double>(), h->d_U.as<double>(), h->d_status.as<int>(), h->d_iters.as<int>(), st);
         if (rc) return rc;
-        CU_OK(cudaEventRecord(h->ev_k[buf], st));
+        if (nu0) CU_OK(cudaEventRecord(h->ev_k[buf], st));
+        else { rc = nu_release(h, nu_which, st); if (rc) return rc; }
         // logs: U_acc[:,k,b] = U(:,0,b), X_acc[:,k,b] = x0, iters
         fmpc_launch_log_step((int)n, (int)m, (int)T, nbatch, K, k, h->d_U.as<double>(), h->d_x0.as<double>(), h->d_iters.as<int>(),
                              h->d_Uacc.as<double>(), h->d_Xacc.as<double>(), h->d_itacc.as<int>(), st);
         CU_OK(cudaGetLastError());
         h->launches += 1;
-        if (k + 1 < K) { rc = upload_nu(k + 1); if (rc) return rc; }
+        if (nu0 && k + 1 < K) { rc = upload_nu(k + 1); if (rc) return rc; }
     }
     CU_OK(cudaEventRecord(h->ev1, st));
     CU_OK(cudaMemcpyAsync(U_acc, h->d_Uacc.p, nb * m * K * 8, cudaMemcpyDeviceToHost, st));

@@ -49,6 +49,9 @@ struct StepArgs {
                                         // any number of concurrent launches of one handle share the per-SM scratch without
                                         // collisions (at most one CTA of this kernel fits an SM)
     long long *prof;                    // optional phase-cycle accumulators (builds with -DFMPC_PROF), else NULL
+    // resident closed loop (fmpc_step_r), honoured by the warp kernel only (the host layer runs separate kernels otherwise):
+    int warm_shift;                     // 1: the warm start is (X0, U0) shifted one stage (stage t <- t + 1, last stage repeated)
+    double *u_first;                    // m x nbatch | NULL: U(:,0) of every instance, compact
 };
 
 // Per-CTA scratch layout (in doubles), computed identically on host and device.
@@ -104,8 +107,13 @@ void fmpc_launch_state_update(const DevSys &S, int nbatch, const double *x, cons
 void fmpc_launch_shift_warm(const DevSys &S, int nbatch, const double *a_k, int a_stride, double *X, double *U,
                             double *x0, double *x0_pre, double *u_prev, int first, void *stream);
 
+void fmpc_launch_shift_inplace(int n, int m, int T, int nbatch, double *X, double *U, void *stream);
+void fmpc_launch_extract_first(int m, int T, int nbatch, const double *U, double *u_first, void *stream);
 void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const double *U, const double *x0, const int *iters,
                           double *Uacc, double *Xacc, int *itacc, void *stream);
+
+// MATLAB default stream MT19937 on the device: appends `count` doubles of the stream at `out` (out == NULL: skips them)
+void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count, void *stream);
 
 // kernel_mma.cu : CTA-per-instance DMMA path (n <= 72)
 int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable

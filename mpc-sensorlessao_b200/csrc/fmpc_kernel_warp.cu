@@ -196,6 +196,7 @@ struct WCtx {
     const int *ydi, *y1i, *y2i;
     // start of the iterate (K_RP pass): warm start arrays of this instance or NULL = midpoint cold start
     const double *U0, *X0, *xmin, *xmax;
+    int sh;                             // 1: read the warm start shifted one stage (resident closed loop), else 0
 
     __device__ __forceinline__ const double *sB() const { return smem; }
     __device__ __forceinline__ const double *sA1() const { return smem + oA1; }
@@ -330,7 +331,7 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
                 if (e < tot) {
                     if (KIND == K_RP) {
                         const int t = e / npad, k = e - t * npad;
-                        if (k < n) a[u] = c.X0 ? c.X0[(size_t)t * n + k] : (c.xmin[k] + c.xmax[k]) / 2;
+                        if (k < n) a[u] = c.X0 ? c.X0[(size_t)min(t + c.sh, T - 1) * n + k] : (c.xmin[k] + c.xmax[k]) / 2;
                     } else if (KIND == K_NEWTON || KIND == K_NORM) {
                         a[u] = pXC[e]; b[u] = pHX[e];
                     } else {
@@ -405,7 +406,7 @@ __device__ __forceinline__ void pass_Cv(const WCtx &c, const double ts, double &
 #pragma unroll
                     for (int tt = 0; tt < TTMAX; ++tt) {
                         const int t = 8 * (tt0 + tt) + gq, j = j4 + q;
-                        bf[h][tt] = (tok[tt] && j < m) ? (c.U0 ? c.U0[(size_t)t * m + j] : (pUmin[j4] + pUmax[j4]) / 2) : 0.0;
+                        bf[h][tt] = (tok[tt] && j < m) ? (c.U0 ? c.U0[(size_t)min(t + c.sh, T - 1) * m + j] : (pUmin[j4] + pUmax[j4]) / 2) : 0.0;
                     }
                 }
             };
@@ -1286,6 +1287,7 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
     c.ws = ws; c.tu = G.TP8 * G.mpad; c.tx = G.TP8 * npad; c.tb = (G.TP8 + 1) * npad; c.bl = (T + 1) * G.NN; c.pp = 0;
     c.ypool = S.ypool; c.ydi = S.ydi; c.y1i = S.y1i; c.y2i = S.y2i;
     c.xmin = S.xmin; c.xmax = S.xmax;
+    c.sh = A.warm_shift ? 1 : 0;
     const int NB = c.NB, mpad = G.mpad;
 
     for (;;) {
@@ -1401,6 +1403,7 @@ __global__ void __launch_bounds__(256, 1) fmpc_solve_kernel_warp(const DevSys S,
                     for (int u = 0; u < 4; ++u) v[u] = (j < m && t0 + u < T) ? pu[(size_t)(t0 + u) * mpad + j] : 0.0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) if (j < m && t0 + u < T) uo[(size_t)(t0 + u) * m + j] = v[u];
+                    if (t0 == 0 && A.u_first && j < m) A.u_first[(size_t)b * m + j] = v[0];
                 }
             }
             for (int t0 = 0; t0 < T; t0 += 8) {

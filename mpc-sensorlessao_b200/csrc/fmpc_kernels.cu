@@ -386,6 +386,27 @@ __global__ void fmpc_shift_warm_kernel(const DevSys S, int nbatch, const double 
     }
 }
 
+// resident closed loop, kernels without the fused variants: warm start <- previous solution shifted one stage, in place
+__global__ void fmpc_shift_inplace_kernel(int n, int m, int T, int nbatch, double *__restrict__ X, double *__restrict__ U)
+{
+    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        double *Ub = U + (size_t)b * m * T, *Xb = X + (size_t)b * n * T;
+        for (int j = threadIdx.x; j < m; j += blockDim.x)
+            for (int t = 0; t + 1 < T; ++t) Ub[(size_t)t * m + j] = Ub[(size_t)(t + 1) * m + j];
+        for (int k = threadIdx.x; k < n; k += blockDim.x)
+            for (int t = 0; t + 1 < T; ++t) Xb[(size_t)t * n + k] = Xb[(size_t)(t + 1) * n + k];
+    }
+}
+// u_first[:,b] = U(:,0,b): the input the loop applies (README.md:589)
+__global__ void fmpc_extract_first_kernel(int m, int T, int nbatch, const double *__restrict__ U, double *__restrict__ u_first)
+{
+    const size_t tot = (size_t)nbatch * m;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = e / m;
+        u_first[e] = U[b * (size_t)m * T + (e - b * m)];
+    }
+}
+
 // closed-loop logs of step k: U_acc[:,k,b] = U(:,0,b) (the applied input), X_acc[:,k,b] = x0[:,b], iters_acc[k,b] = iters[b]
 __global__ void fmpc_log_step_kernel(int n, int m, int T, int nbatch, int K, int k, const double *__restrict__ U,
                                      const double *__restrict__ x0, const int *__restrict__ iters, double *__restrict__ Uacc,
@@ -399,6 +420,67 @@ __global__ void fmpc_log_step_kernel(int n, int m, int T, int nbatch, int K, int
         else Xacc[(b * K + k) * n + (j - m)] = x0[b * n + (j - m)];
         if (j == 0 && itacc) itacc[b * K + k] = iters[b];
     }
+}
+
+// =============================================================================================
+// MATLAB's default global stream on the device: `nu = rand(length(b),1)` (inf_newton_solver.m:2) is MT19937 seeded with
+// 5489, doubles by genrand_res53.  ONE CTA walks the stream: the recurrence
+//     x[k+624] = x[k+397] ^ twist(x[k], x[k+1])
+// is 227-way parallel (the newest operand lies 227 words back), so a 624-word block is regenerated in three barrier-separated
+// phases (227 + 227 + 170 words) from the previous block into the other half of a double buffer; tempering and the conversion
+// of the finished block to doubles need no barrier of their own (they only read it).  state[0..623] = current block,
+// state[624] = next unread word (always even: a double takes two words and 624 is even, so pairs never straddle blocks).
+// Also used without output (out == NULL) to skip `count` doubles.
+// =============================================================================================
+__device__ __forceinline__ unsigned mt_twist(unsigned a, unsigned b)
+{
+    const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+}
+__device__ __forceinline__ unsigned mt_temper(unsigned y)
+{
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+}
+__global__ void __launch_bounds__(256, 1) fmpc_mt_fill_kernel(unsigned *__restrict__ state, double *__restrict__ out,
+                                                              unsigned long long count)
+{
+    __shared__ unsigned mt[2][624];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 624; i += 256) mt[0][i] = state[i];
+    int idx = (int)state[624], cur = 0;
+    unsigned long long done = 0;
+    __syncthreads();
+    while (done < count) {
+        if (idx >= 624) {
+            const unsigned *o = mt[cur];
+            unsigned *w = mt[cur ^ 1];
+            if (tid < 227) w[tid] = o[tid + 397] ^ mt_twist(o[tid], o[tid + 1]);
+            __syncthreads();
+            if (tid < 227) w[tid + 227] = w[tid] ^ mt_twist(o[tid + 227], o[tid + 228]);
+            __syncthreads();
+            if (tid < 169) w[tid + 454] = w[tid + 227] ^ mt_twist(o[tid + 454], o[tid + 455]);
+            if (tid == 169) w[623] = w[396] ^ mt_twist(o[623], w[0]);
+            __syncthreads();
+            cur ^= 1;
+            idx = 0;
+        }
+        const unsigned long long left = count - done;
+        const int avail = (624 - idx) >> 1;
+        const int take = (left < (unsigned long long)avail) ? (int)left : avail;
+        if (out) {
+            const unsigned *o = mt[cur] + idx;
+            for (int t = tid; t < take; t += 256) {
+                const unsigned a = mt_temper(o[2 * t]) >> 5, b = mt_temper(o[2 * t + 1]) >> 6;
+                out[done + t] = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+            }
+        }
+        idx += 2 * take;
+        done += take;
+    }
+    __syncthreads();
+    for (int i = tid; i < 624; i += 256) state[i] = mt[cur][i];
+    if (tid == 0) state[624] = (unsigned)idx;
 }
 
 // =============================================================================================
@@ -462,4 +544,25 @@ void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const d
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
     fmpc_log_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, T, nbatch, K, k, U, x0, iters, Uacc, Xacc, itacc);
+}
+
+void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count, void *stream)
+{
+    fmpc_mt_fill_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, out, count);
+}
+
+void fmpc_launch_shift_inplace(int n, int m, int T, int nbatch, double *X, double *U, void *stream)
+{
+    int grid = nbatch < 148 * 8 ? nbatch : 148 * 8;
+    if (grid < 1) grid = 1;
+    fmpc_shift_inplace_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(n, m, T, nbatch, X, U);
+}
+
+void fmpc_launch_extract_first(int m, int T, int nbatch, const double *U, double *u_first, void *stream)
+{
+    const size_t tot = (size_t)nbatch * m;
+    int grid = (int)((tot + 255) / 256);
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    fmpc_extract_first_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, T, nbatch, U, u_first);
 }

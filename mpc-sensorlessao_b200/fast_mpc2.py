@@ -195,6 +195,39 @@ class FastMPCBatch:
                                         C.cast(C.byref(tel), C.c_void_p)))
         return dict(X=X, U=U, status=status, iters=iters, telapsed=tel.value)
 
+    def step_resident(self, x0, x0_pre=None, w=None, xf=None, nu0=None, u_prev=None, reset=False, full=False, params=None,
+                      kappa=0.01, niters=5, ls_max=0):
+        """One step of a closed loop whose solver state stays on the device (`fmpc_step_r`): warm start = the previous
+        call's solution shifted one stage, x0_pre defaults to the previous x0, u_prev to the previous U(:,0).
+        Only x0 goes in and U(:,0) comes out (README.md:589) unless `full`.  `reset=True` starts a loop (cold start).
+        Returns dict(u0 (nb, m), status, iters, telapsed[, X, U])."""
+        n, m, T = self.n, self.m, self.T
+        x0 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64))
+        if x0.ndim == 1:
+            x0 = x0.reshape(1, -1)
+        nb = x0.shape[0]
+        if x0.shape[1] != n:
+            raise ValueError("The equality state dynamics matrix size does not match")
+        x0_pre = self._inst(x0_pre, n, "x0_pre", nb)
+        w = self._inst(w, T * n, "w", nb)
+        xf = self._inst(xf, n, "xf", nb)
+        u_prev = self._inst(u_prev, m, "u_prev", nb)
+        nu0 = self._inst(nu0, (T + (1 if xf is not None else 0)) * n, "nu0", nb)
+        p = params if params is not None else self.params(kappa, niters, ls_max)
+        u0 = np.empty((nb, m))
+        X = np.empty((nb, T, n)) if full else None
+        U = np.empty((nb, T, m)) if full else None
+        status = np.zeros(nb, dtype=np.int32)
+        iters = np.zeros(nb, dtype=np.int32)
+        tel = C.c_double(0.0)
+        check(self._L.fmpc_step_r(self._h, C.byref(p), nb, 1 if reset else 0, _ptr(x0), _ptr(x0_pre), _ptr(u_prev), _ptr(w),
+                                  _ptr(xf), _ptr(nu0), _ptr(u0), _ptr(X), _ptr(U), _ptr(status), _ptr(iters),
+                                  C.cast(C.byref(tel), C.c_void_p)))
+        out = dict(u0=u0, status=status, iters=iters, telapsed=tel.value)
+        if full:
+            out["X"], out["U"] = X, U
+        return out
+
     def state_update(self, x, x_pre, u, w=None):
         """x+ = A1 x + A2 x- + B u (+ w) per instance (VAR_2/fast_mpc_eq_const.m:39-47 as a recurrence)."""
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))

@@ -246,6 +246,115 @@ def test_closed_loop_matches_host_driven_loop(pk, fref):
         assert np.array_equal(out["iters"][:, k], ref["iters"])
 
 
+def test_resident_steps_match_oracle_driven_loop(pk, fref):
+    """K `fmpc_step_r` calls (state on the device: only x0 in, U(:,0) out) == the loop driven from the host through the
+    oracle with the warm start shifted by hand (README.md:444-626 around the solve)."""
+    from mpc_sensorlessao_b200 import synth
+    p = synth.make_problem(3, 6, m1=4)            # n = 10, m = 16
+    nb, K = 5, 6
+    a = synth.aberrations(p, nb, K, seed=7)
+    nu = np.random.RandomState(2).rand(K, nb, p.T * p.n)
+    hb = pk.FastMPCBatch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, max_batch=nb)
+    with pytest.raises(pk.FmpcError) as ei:       # nothing resident yet: the first call must reset
+        hb.step_resident(a[:, 0], nu0=nu[0], niters=3)
+    assert ei.value.code == -12
+    u_prev = np.zeros((nb, p.m)); x0 = np.zeros((nb, p.n)); U = X = None
+    for k in range(K):
+        x0_pre = x0 if k else np.zeros((nb, p.n))
+        x0 = a[:, k] + u_prev @ p.B.T
+        out = hb.step_resident(x0, nu0=nu[k], reset=(k == 0), full=(k % 2 == 1), niters=3)
+        c = dict(n=p.n, m=p.m, T=p.T, nb=nb, A1=p.A1, A2=p.A2, B=p.B, Q=p.Q, R=p.R, Qf=p.Qf, u_min=p.u_min, u_max=p.u_max,
+                 x_min=p.x_min, x_max=p.x_max, x0=x0, x0_pre=x0_pre, w=None, xf=None, nu0=nu[k],
+                 X0=None if k == 0 else np.concatenate([X[:, 1:], X[:, -1:]], axis=1),
+                 U0=None if k == 0 else np.concatenate([U[:, 1:], U[:, -1:]], axis=1))
+        ref = ref_solve(fref, c, 3, 0.01)
+        U, X = ref["U"], ref["X"]
+        u_prev = U[:, 0]
+        assert relerr(out["u0"], u_prev) < 1e-8, k
+        assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["status"], ref["status"])
+        if "U" in out:
+            assert relerr(out["U"], U) < 1e-8 and relerr(out["X"], X) < 1e-8
+            assert np.array_equal(out["U"][:, 0], out["u0"])
+    hb.close()
+
+
+@pytest.mark.parametrize("shape", [(28, 144, 20, 300), (40, 12, 5, 4)], ids=["warp_kernel", "cta_kernel"])
+def test_resident_step_equals_full_surface_step(pk, shape):
+    """Bit-for-bit: fmpc_step_r == fmpc_step fed with the previous outputs shifted one stage and the previous x0
+    (both the fused warp-kernel variant and the separate shift / extract kernels of the other solve kernels)."""
+    n, m, T, nb = shape
+    c = small_problem(31, n, m, T, nb, 0.5, warm=False)
+    c["w"] = None
+    rs = np.random.RandomState(3)
+    hb = make_handle(pk, c)
+    hr = make_handle(pk, c)
+    X = U = None
+    x0_pre = np.zeros((nb, n))
+    for k in range(3):
+        x0 = rs.randn(nb, n) * 0.3
+        nu = rs.rand(nb, T * n)
+        ref = hb.step(x0, x0_pre, None, None, None if k == 0 else np.concatenate([X[:, 1:], X[:, -1:]], axis=1),
+                      None if k == 0 else np.concatenate([U[:, 1:], U[:, -1:]], axis=1), nu, niters=4)
+        out = hr.step_resident(x0, nu0=nu, reset=(k == 0), full=True, niters=4)
+        X, U = ref["X"], ref["U"]
+        assert np.array_equal(out["U"], U) and np.array_equal(out["X"], X) and np.array_equal(out["u0"], U[:, 0])
+        assert np.array_equal(out["iters"], ref["iters"])
+        x0_pre = x0
+    hb.close(); hr.close()
+
+
+def test_pinned_and_pageable_host_buffers_agree(pk):
+    """fmpc_step stages pageable caller buffers through its own pinned ring (copy threads); pinned buffers go to the DMA
+    engines directly.  Same bits either way, for a batch cut into several chunks."""
+    import ctypes as C
+    import torch
+    c = small_problem(51, 28, 144, 20, 1300, 0.5, warm=True)
+    hb = make_handle(pk, c)
+    ref = gpu_solve(pk, c, 3, 0.01, hb=hb)                      # numpy arrays: pageable
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    t = {k: pin(c[k]) for k in ("x0", "x0_pre", "w", "X0", "U0", "nu0")}
+    X, U = pin(np.zeros_like(ref["X"])), pin(np.zeros_like(ref["U"]))
+    it = torch.zeros(c["nb"], dtype=torch.int32).pin_memory()
+    p = hb.params(0.01, 3, 0)
+    vp = lambda a: C.c_void_p(a.data_ptr())
+    rc = hb._L.fmpc_step(hb._h, C.byref(p), c["nb"], vp(t["x0"]), vp(t["x0_pre"]), None, vp(t["w"]), None, vp(t["X0"]), vp(t["U0"]),
+                         vp(t["nu0"]), vp(X), vp(U), None, vp(it), None)
+    assert rc == 0
+    assert np.array_equal(X.numpy(), ref["X"]) and np.array_equal(U.numpy(), ref["U"]) and np.array_equal(it.numpy(), ref["iters"])
+    hb.close()
+
+
+def test_matlab_stream_on_device_across_batch_sizes(pk):
+    """nu0 = NULL consumes ONE MT19937(5489) stream in order whatever the sequence of calls and batch sizes
+    (device generator running one call ahead, left-overs carried over): every call equals the explicit-nu0 call."""
+    c = small_problem(41, 6, 4, 5, 9, 0.3, warm=True)
+    T, n = c["T"], c["n"]
+    stream = np.random.RandomState(5489).random_sample(64 * T * n)
+    hb = make_handle(pk, c)
+    hx = make_handle(pk, c)
+    pos = 0
+    for nbk in (9, 9, 4, 9, 1, 7, 7):
+        sub = {k: (v[:nbk] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == c["nb"] and k in
+                   ("x0", "x0_pre", "w", "X0", "U0") else v) for k, v in c.items()}
+        sub["nb"] = nbk
+        sub["nu0"] = None
+        out = gpu_solve(pk, sub, 4, 0.01, hb=hb)
+        sub["nu0"] = stream[pos:pos + nbk * T * n].reshape(nbk, T * n)
+        pos += nbk * T * n
+        ref = gpu_solve(pk, sub, 4, 0.01, hb=hx)
+        assert np.array_equal(out["U"], ref["U"]) and np.array_equal(out["iters"], ref["iters"])
+    # the closed loop draws from the same stream: K steps of nb instances each
+    from mpc_sensorlessao_b200 import synth
+    p = synth.make_problem(3, 6, m1=4)
+    a = synth.aberrations(p, 3, 4, seed=5)
+    h1 = pk.FastMPCBatch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, max_batch=3)
+    h2 = pk.FastMPCBatch(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, max_batch=3)
+    o1 = h1.closed_loop(a, nu0=None, niters=3)
+    o2 = h2.closed_loop(a, nu0=np.random.RandomState(5489).random_sample(4 * 3 * p.T * p.n).reshape(4, 3, -1), niters=3)
+    assert np.array_equal(o1["U_acc"], o2["U_acc"]) and np.array_equal(o1["iters"], o2["iters"])
+    h1.close(); h2.close(); hb.close(); hx.close()
+
+
 # ---- BASELINE.json full size: properties that need no oracle ---------------------------------
 @pytest.fixture(scope="module")
 def c2(pk):
