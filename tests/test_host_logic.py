@@ -111,19 +111,45 @@ def test_side_entry_points_validate_before_cuda(pk):
 
 
 def test_library_mt19937_is_matlabs_default_stream(tmp_path):
-    """The library's own generator (nu0 = NULL => rand(length(b),1), inf_newton_solver.m:2) is compiled out of
-    csrc/fmpc_api.cu on the host and compared with MT19937(5489) 53-bit doubles = MATLAB's default stream."""
+    """nu0 = NULL => rand(length(b),1) (inf_newton_solver.m:2) from MATLAB's default stream MT19937(5489).
+    The host seeds the state (struct MT19937 of csrc/fmpc_api.cu, compiled here); the stream itself is generated on the
+    device in three barrier-separated phases per 624-word block (fmpc_mt_fill_kernel) -- restated here in numpy with the
+    kernel's index ranges and compared with numpy's MT19937; the kernel itself is checked by the -m gpu tests."""
     import subprocess
     src = open(os.path.join(ROOT, "mpc-sensorlessao_b200", "csrc", "fmpc_api.cu")).read()
     a = src.index("struct MT19937 {")
     b = src.index("#define CU_OK", a)
     code = ("#include <cstdint>\n#include <cstdio>\n" + src[a:b] +
-            "\nint main(){ MT19937 g; for (int i = 0; i < 4000; ++i) printf(\"%.17g\\n\", g.rand53()); return 0; }\n")
+            "\nint main(){ MT19937 g(5489u); for (int i = 0; i < 624; ++i) printf(\"%u\\n\", g.mt[i]); return 0; }\n")
     cpp, exe = tmp_path / "mt.cpp", tmp_path / "mt"
     cpp.write_text(code)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call([cxx, "-O2", "-o", str(exe), str(cpp)])
-    out = np.array([float(x) for x in subprocess.check_output([str(exe)]).split()])
-    ref = np.random.RandomState(5489).random_sample(4000)
+    seed_state = np.array([int(x) for x in subprocess.check_output([str(exe)]).split()], dtype=np.uint32)
+    assert np.array_equal(seed_state, np.random.RandomState(5489).get_state()[1])
+
+    def twist(a, b):
+        y = (a & np.uint32(0x80000000)) | (b & np.uint32(0x7fffffff))
+        return (y >> np.uint32(1)) ^ (np.where(y & np.uint32(1), np.uint32(0x9908b0df), np.uint32(0)))
+
+    def temper(y):
+        y = y ^ (y >> np.uint32(11)); y = y ^ ((y << np.uint32(7)) & np.uint32(0x9d2c5680))
+        y = y ^ ((y << np.uint32(15)) & np.uint32(0xefc60000)); return y ^ (y >> np.uint32(18))
+
+    o, out = seed_state.copy(), []
+    for _ in range(7):                                  # 7 blocks = 2184 doubles
+        w = np.zeros(624, dtype=np.uint32)
+        t = np.arange(227)
+        w[t] = o[t + 397] ^ twist(o[t], o[t + 1])                       # phase 1: tid < 227
+        w[t + 227] = w[t] ^ twist(o[t + 227], o[t + 228])               # phase 2
+        t = np.arange(169)
+        w[t + 454] = w[t + 227] ^ twist(o[t + 454], o[t + 455])         # phase 3: tid < 169 ...
+        w[623] = w[396] ^ twist(o[623:624], w[0:1])[0]                  # ... and tid == 169
+        y = temper(w)
+        out.append(((y[0::2] >> np.uint32(5)).astype(np.float64) * 67108864.0 + (y[1::2] >> np.uint32(6)).astype(np.float64))
+                   * (1.0 / 9007199254740992.0))
+        o = w
+    out = np.concatenate(out)
+    ref = np.random.RandomState(5489).random_sample(out.size)
     assert np.array_equal(out, ref)
     assert abs(out[0] - 0.8147236863931789) < 1e-16 and abs(out[1] - 0.9057919370756192) < 1e-16       # MATLAB: rand after start-up
