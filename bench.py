@@ -570,6 +570,64 @@ def measure_closed_loop(cx, p, nb, K):
             "newton_iters_per_solve": its / (nb * K), "roofline_frac": its * F / out["telapsed"] / 1e12 / cx.peak}
 
 
+def run_single_process(args):
+    """--single-process: ONE process drives all --gpus devices through the library's own multi-GPU entry points
+    (fmpc_multi_step_r: one handle + host thread per device, contiguous shards) -- the path a MATLAB caller gets.
+    Host buffers only, so the line's `value` is the end-to-end rate; per-device statistics come back over NCCL."""
+    import torch
+    import mpc_sensorlessao_b200 as pk
+    from mpc_sensorlessao_b200 import synth
+    name = args.config if args.config in CONFIGS else "c2"
+    N, T, nbc, ub, scaling, _ = CONFIGS[name]
+    G = args.gpus
+    nb_gpu = args.instances or nbc or 65536 // G
+    nb = nb_gpu * G
+    p = synth.make_problem(N, T, u_bound=ub)
+    n, m = p.n, p.m
+    K, W = args.steps, max(args.warmup, 3)
+    hm = pk.FastMPCMulti(p.A1, p.A2, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, T, p.x_min, p.x_max, max_batch=nb, ngpus=G)
+    params = hm.params(KAPPA, NITERS, 0)
+    KT = PRE + W + K
+    noise = np.concatenate([loop_noise(p, nb_gpu, KT + 1, seed=100 + 10 * g) for g in range(G)], axis=0)
+    x0s = [torch.empty((nb, n), dtype=torch.float64).pin_memory() for _ in range(KT)]
+    hu = torch.empty((nb, m), dtype=torch.float64).pin_memory()
+    hs, hi = torch.empty(nb, dtype=torch.int32).pin_memory(), torch.empty(nb, dtype=torch.int32).pin_memory()
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def step(k):
+        rc = hm._L.fmpc_multi_step_r(hm._h, C.byref(params), nb, 1 if k == 0 else 0, ptr(x0s[k]), None, None, None, None, None,
+                                     ptr(hu), None, None, ptr(hs), ptr(hi), None)
+        if rc:
+            raise pk.FmpcError(rc, pk.strerror(rc))
+    x = noise[:, 0].copy(); xp = np.zeros((nb, n))
+    for k in range(KT):                     # pass 0: the plant on the host records the x0 sequence
+        x0s[k].numpy()[:] = x
+        step(k)
+        xn = x @ p.A1.T + xp @ p.A2.T + hu.numpy() @ p.B.T + noise[:, k + 1]
+        xp, x = x, xn
+    for k in range(PRE + W):
+        step(k)
+    its = 0
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(PRE + W + i)
+        its += int(hi.numpy().sum())
+    dt = time.perf_counter() - t0
+    st = hm.stats(use_nccl=True)
+    launches = hm.launch_count
+    hm.close()
+    F = f_newton(n, m, T)
+    line = {"metric": "fastmpc_solves_per_sec", "value": nb * K / dt, "unit": "solves/s", "n_gpus": G, "steps": K, "warmup": W,
+            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_desc(name, p, nb_gpu, G, "loop"),
+            "mode": "single process, fmpc_multi_step_r (one handle + host thread per device), pinned host buffers, wall clock",
+            "e2e": {"value": nb * K / dt, "unit": "solves/s", "h2d_bytes_per_step": nb * n * 8, "d2h_bytes_per_step": nb * (m * 8 + 8),
+                    "api": "fmpc_multi_step_r"},
+            "newton_iters_per_solve": its / (nb * K), "aggregate_tflops": its * F / dt / 1e12, "gpu_launches": launches,
+            "per_device_stats_last_step": st}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -580,6 +638,8 @@ def main():
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the side workloads reported under `extra`")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus devices from ONE process through fmpc_multi_* (not under torchrun)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -588,6 +648,9 @@ def main():
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)
+    if args.single_process:
+        run_single_process(args)
+        return
 
     import torch
     import torch.distributed as dist

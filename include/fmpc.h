@@ -133,7 +133,10 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch,
               double *X, double *U, int *status, int *iters, double *telapsed);
 
 /* Same solve on DEVICE buffers, asynchronous on `stream` (no host sync, no allocation).
- * X/U may alias X0/U0 (in-place warm start).  nu0 must be given (device).  */
+ * X/U may alias X0/U0 (in-place warm start).  nu0 must be given (device).
+ * ONE solve in flight per handle: every launch of a handle shares its instance counter and scratch slots, so a second
+ * fmpc_step_d / fmpc_step_r_d on the same handle must be issued on the same stream (or after the first has completed);
+ * use one handle per stream for concurrent solves.  The host-buffer entry points block, so they are safe as they are. */
 int fmpc_step_d(fmpc_handle *h, const fmpc_params *p, int nbatch,
                 const double *x0, const double *x0_pre, const double *u_prev,
                 const double *w, const double *xf,
@@ -207,6 +210,40 @@ int fmpc_state_update_d(fmpc_handle *h, int nbatch, const double *x, const doubl
 int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K,
                      const double *a, const double *nu0,
                      double *U_acc, double *X_acc, int *iters_acc, double *telapsed);
+
+/* Re-seeds the handle's MT19937 stream (the source of nu0 == NULL dual starts); 5489 = MATLAB's `rng default`. */
+int fmpc_seed_stream(fmpc_handle *h, unsigned seed);
+
+/* ---- all GPUs of the box behind ONE blocking call ------------------------------------------------------
+ * One handle, one stream set and one host thread per device, in a single process: the batch is cut into contiguous shards
+ * of ceil(nbatch / G) instances, every device solves its shard (no inter-GPU traffic: instances are independent), the
+ * call returns when all shards are on the host.  Same arguments and results as fmpc_step / fmpc_step_r -- with explicit
+ * nu0 bit-identical to a single-device call (tests/test_gpu_multi.py).  nu0 == NULL draws from one MT19937 stream PER
+ * DEVICE (device 0: MATLAB's default stream, device g: seed 5489 + g): one sequential stream cannot feed several GPUs.
+ *   ngpus   <= 0: every usable sm_100 device          devices  NULL: 0 .. ngpus-1 */
+typedef struct fmpc_multi fmpc_multi;
+typedef struct fmpc_multi_stats {          /* one 64-byte record per device, all doubles (it travels over ncclAllGather) */
+    double device, n_solves, device_seconds, newton_iters, status_hist[4];   /* FMPC_ST_OK, _EARLY_EXIT, _NOT_PD, _LS_MAX + _NONFINITE */
+} fmpc_multi_stats;
+int  fmpc_multi_create(fmpc_multi **out, const fmpc_sys *sys, int max_batch, int ngpus, const int *devices);
+void fmpc_multi_destroy(fmpc_multi *M);
+int  fmpc_multi_ngpus(const fmpc_multi *M);
+/* shard of device slot g for a batch of nbatch instances: first instance and count */
+int  fmpc_multi_shard(const fmpc_multi *M, int nbatch, int g, int *first, int *count);
+fmpc_handle *fmpc_multi_handle(fmpc_multi *M, int g);          /* the per-device handle (e.g. for fmpc_kernel_kind) */
+int  fmpc_multi_step(fmpc_multi *M, const fmpc_params *p, int nbatch,
+                     const double *x0, const double *x0_pre, const double *u_prev,
+                     const double *w, const double *xf,
+                     const double *X0, const double *U0, const double *nu0,
+                     double *X, double *U, int *status, int *iters, double *telapsed /* max over devices */);
+int  fmpc_multi_step_r(fmpc_multi *M, const fmpc_params *p, int nbatch, int flags,
+                       const double *x0, const double *x0_pre, const double *u_prev,
+                       const double *w, const double *xf, const double *nu0,
+                       double *u0, double *X, double *U, int *status, int *iters, double *telapsed);
+/* Per-device statistics of the last step (solves, device seconds, Newton iterations, status histogram).  use_nccl != 0: gathered with ncclAllGather over NVLink (ncclCommInitAll in this process, libnccl.so.2
+ * loaded with dlopen) -- the only collective of the path; else, or if NCCL is not available, read by the host.
+ * Returns the number of records written to out[0 .. G-1]; *used_nccl tells which way they came. */
+int  fmpc_multi_last_stats(fmpc_multi *M, fmpc_multi_stats *out, int use_nccl, int *used_nccl);
 
 /* Dimensions the handle was created with (any pointer may be NULL). */
 int fmpc_get_dims(const fmpc_handle *h, int *n, int *m, int *T);

@@ -44,7 +44,8 @@ ABI_SYMBOLS = [
     "fmpc_default_params", "fmpc_device_count", "fmpc_create", "fmpc_destroy", "fmpc_step", "fmpc_step_d",
     "fmpc_step_r", "fmpc_step_r_d", "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
-    "fmpc_fp64_peak", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
+    "fmpc_fp64_peak", "fmpc_seed_stream", "fmpc_multi_create", "fmpc_multi_destroy", "fmpc_multi_ngpus", "fmpc_multi_shard",
+    "fmpc_multi_handle", "fmpc_multi_step", "fmpc_multi_step_r", "fmpc_multi_last_stats", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
     "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count", "var_identify",
 ]
@@ -88,6 +89,17 @@ def load_library():
     L.fmpc_step_d.argtypes = step_args + [vp]              # ..., status, iters, stream
     L.fmpc_step_r.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6 + [vp] * 6
     L.fmpc_step_r_d.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6 + [vp] * 6
+    L.fmpc_seed_stream.argtypes = [vp, C.c_uint]
+    L.fmpc_multi_create.argtypes = [C.POINTER(vp), C.POINTER(FmpcSys), C.c_int, C.c_int, vp]
+    L.fmpc_multi_destroy.argtypes = [vp]
+    L.fmpc_multi_destroy.restype = None
+    L.fmpc_multi_ngpus.argtypes = [vp]
+    L.fmpc_multi_shard.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.fmpc_multi_handle.argtypes = [vp, C.c_int]
+    L.fmpc_multi_handle.restype = vp
+    L.fmpc_multi_step.argtypes = step_args + [vp]
+    L.fmpc_multi_step_r.argtypes = [vp, C.POINTER(FmpcParams), C.c_int, C.c_int] + [vp] * 6 + [vp] * 6
+    L.fmpc_multi_last_stats.argtypes = [vp, vp, C.c_int, vp]
     L.fmpc_step_z.argtypes = [vp, C.POINTER(FmpcParams), C.c_int] + [vp] * 8 + [vp, vp, vp]
     L.fmpc_frontend.argtypes = [vp, C.c_int, C.POINTER(FmpcParams), C.c_double, C.c_double, C.c_int] + [vp] * 10 + [vp, vp, vp]
     L.fmpc_frontend_nouter.argtypes = [vp, C.c_int]

@@ -485,7 +485,11 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
         const size_t wsb = (size_t)h->cfg.slots * h->cfg.ws_stride * sizeof(double);
         if (h->ws.ensure(wsb) || h->counters.ensure(256 * fmpc_handle::MAX_CHUNKS)) ok = false;
         if (ok && cudaMemset(h->counters.p, 0, 256 * fmpc_handle::MAX_CHUNKS) != cudaSuccess) ok = false;
-        if (ok && h->cfg.use_mma == 2 && !getenv("FMPC_NO_SMID_SLOTS")) h->smid_slots = fmpc_warp_smid_slots_ok(h->cfg, device);
+        // SM-id indexed scratch slots are OPT-IN (FMPC_SMID_SLOTS=1): %smid is not stable under compute preemption / MPS
+        // time-slicing / a debugger, where a migrated CTA would share a slot with a newly scheduled one.  The default keeps the
+        // disjoint slot_base partitions of step_device.
+        if (ok && h->cfg.use_mma == 2 && getenv("FMPC_SMID_SLOTS") && atoi(getenv("FMPC_SMID_SLOTS")) > 0)
+            h->smid_slots = fmpc_warp_smid_slots_ok(h->cfg, device);
         // the warp kernel relies on never-written padding columns of its scratch staying zero
         if (ok && cudaMemset(h->ws.p, 0, wsb) != cudaSuccess) ok = false;
     }
@@ -514,6 +518,20 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     }
     if (!ok) { fmpc_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
+    return FMPC_OK;
+}
+
+int fmpc_seed_stream(fmpc_handle *h, unsigned seed)
+{
+    if (!h) return FMPC_ERR_NULL;
+    CU_OK(cudaSetDevice(h->device));
+    CU_OK(cudaStreamSynchronize(h->s_gen));         // doubles generated ahead from the old state are dropped
+    MT19937 g(seed);
+    uint32_t st[625];
+    std::memcpy(st, g.mt, sizeof(g.mt));
+    st[624] = 624u;
+    CU_OK(cudaMemcpy(h->d_mt.p, st, sizeof(st), cudaMemcpyHostToDevice));
+    h->nu_have = 0;
     return FMPC_OK;
 }
 

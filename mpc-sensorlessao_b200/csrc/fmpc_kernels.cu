@@ -424,15 +424,19 @@ __global__ void fmpc_log_step_kernel(int n, int m, int T, int nbatch, int K, int
 
 // =============================================================================================
 // MATLAB's default global stream on the device: `nu = rand(length(b),1)` (inf_newton_solver.m:2) is MT19937 seeded with
-// 5489, doubles by genrand_res53.  ONE CTA walks the stream: the recurrence
-//     x[k+624] = x[k+397] ^ twist(x[k], x[k+1])
-// is 227-way parallel (the newest operand lies 227 words back), so a 624-word block is regenerated in three barrier-separated
-// phases (227 + 227 + 170 words) from the previous block into the other half of a double buffer; tempering and the conversion
-// of the finished block to doubles need no barrier of their own (they only read it).  state[0..623] = current block,
-// state[624] = next unread word (always even: a double takes two words and 624 is even, so pairs never straddle blocks).
-// Also used without output (out == NULL) to skip `count` doubles.
+// 5489, doubles by genrand_res53.  ONE CTA walks the stream (it is one dependency chain).  The recurrence
+//     x[k+624] = x[k+397] ^ f(x[k], x[k+1])
+// reaches back 227 words, which would cost three barrier-separated phases per 624-word block; substituting the recurrence
+// into itself expresses EVERY word of the next block by words of the current one,
+//     n[e] = o[e+397] ^ f(o[e],o[e+1])                                                        e <  227
+//     n[e] = o[e+170] ^ f(o[e-227],o[e-226]) ^ f(o[e],o[e+1])                           227 <= e <  454
+//     n[e] = o[e- 57] ^ f(o[e-454],o[e-453]) ^ f(o[e-227],o[e-226]) ^ f(o[e],o[e+1])    454 <= e <  623
+//     n[623] = n[396] ^ f(o[623], n[0])      (both expanded the same way)
+// so a block costs ONE barrier: all threads form the next block and temper / store the current one from the same reads.
+// state[0..623] = current block, state[624] = next unread word (always even: a double takes two words and 624 is even, so
+// pairs never straddle blocks).  out == NULL skips `count` doubles.
 // =============================================================================================
-__device__ __forceinline__ unsigned mt_twist(unsigned a, unsigned b)
+__device__ __forceinline__ unsigned mt_f(unsigned a, unsigned b)
 {
     const unsigned y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
@@ -442,43 +446,55 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y)
     y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
     return y;
 }
+__device__ __forceinline__ unsigned mt_next_word(const unsigned *o, const int e)
+{
+    if (e < 227) return o[e + 397] ^ mt_f(o[e], o[e + 1]);
+    if (e < 454) return o[e + 170] ^ mt_f(o[e - 227], o[e - 226]) ^ mt_f(o[e], o[e + 1]);
+    if (e < 623) return o[e - 57] ^ mt_f(o[e - 454], o[e - 453]) ^ mt_f(o[e - 227], o[e - 226]) ^ mt_f(o[e], o[e + 1]);
+    const unsigned n0 = o[397] ^ mt_f(o[0], o[1]);
+    const unsigned n396 = o[566] ^ mt_f(o[169], o[170]) ^ mt_f(o[396], o[397]);
+    return n396 ^ mt_f(o[623], n0);
+}
 __global__ void __launch_bounds__(256, 1) fmpc_mt_fill_kernel(unsigned *__restrict__ state, double *__restrict__ out,
                                                               unsigned long long count)
 {
-    __shared__ unsigned mt[2][624];
+    __shared__ __align__(16) unsigned mt[2][624];
     const int tid = threadIdx.x;
     for (int i = tid; i < 624; i += 256) mt[0][i] = state[i];
     int idx = (int)state[624], cur = 0;
     unsigned long long done = 0;
     __syncthreads();
+    if (idx >= 624 && count > 0) {          // nothing unread in the stored block: form the first one
+        for (int e = tid; e < 624; e += 256) mt[1][e] = mt_next_word(mt[0], e);
+        __syncthreads();
+        cur = 1; idx = 0;
+    }
     while (done < count) {
-        if (idx >= 624) {
-            const unsigned *o = mt[cur];
-            unsigned *w = mt[cur ^ 1];
-            if (tid < 227) w[tid] = o[tid + 397] ^ mt_twist(o[tid], o[tid + 1]);
-            __syncthreads();
-            if (tid < 227) w[tid + 227] = w[tid] ^ mt_twist(o[tid + 227], o[tid + 228]);
-            __syncthreads();
-            if (tid < 169) w[tid + 454] = w[tid + 227] ^ mt_twist(o[tid + 454], o[tid + 455]);
-            if (tid == 169) w[623] = w[396] ^ mt_twist(o[623], w[0]);
-            __syncthreads();
-            cur ^= 1;
-            idx = 0;
-        }
+        // invariant: block `cur` holds unread words from idx on
         const unsigned long long left = count - done;
         const int avail = (624 - idx) >> 1;
         const int take = (left < (unsigned long long)avail) ? (int)left : avail;
+        const bool more = left > (unsigned long long)avail;          // another block is needed after this one
+        const unsigned *o = mt[cur];
+        if (more) {
+            unsigned *w = mt[cur ^ 1];
+            for (int e = tid; e < 624; e += 256) w[e] = mt_next_word(o, e);
+        }
         if (out) {
-            const unsigned *o = mt[cur] + idx;
             for (int t = tid; t < take; t += 256) {
-                const unsigned a = mt_temper(o[2 * t]) >> 5, b = mt_temper(o[2 * t + 1]) >> 6;
-                out[done + t] = ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+                const uint2 y = *reinterpret_cast<const uint2 *>(o + idx + 2 * t);      // idx is even: 8-byte aligned
+                const unsigned a = mt_temper(y.x) >> 5, b = mt_temper(y.y) >> 6;
+                // (a 2^26 + b) 2^-53 without integer -> double conversions: both pieces are exact in the mantissa of 2^52 + v
+                const double da = __longlong_as_double(0x4330000000000000ll | (long long)a) - 4503599627370496.0;
+                const double db = __longlong_as_double(0x4330000000000000ll | (long long)b) - 4503599627370496.0;
+                out[done + t] = (da * 67108864.0 + db) * (1.0 / 9007199254740992.0);
             }
         }
+        __syncthreads();
         idx += 2 * take;
         done += take;
+        if (more) { cur ^= 1; idx = 0; }
     }
-    __syncthreads();
     for (int i = tid; i < 624; i += 256) state[i] = mt[cur][i];
     if (tid == 0) state[624] = (unsigned)idx;
 }

@@ -77,6 +77,28 @@ class FastMPCBatch:
         self.n, self.m = self._B.shape
         self.T = int(T)
         n, m = self.n, self.m
+        # the C side cannot see array sizes: the reference's dimension checks, with its error strings
+        if self._Q.shape != (n, n) or self._Qf.shape != (n, n):
+            raise ValueError("State stage cost must a square matrix")                       # fast_mpc_objective.m:17-19
+        if self._R.shape != (m, m):
+            raise ValueError("Control stage cost must a square matrix")                     # :20-21
+        if self._A1.shape != (n, n) or (self._A2 is not None and self._A2.shape != (n, n)):
+            raise ValueError("The equality state dynamics matrix size does not match")      # fast_mpc_eq_const.m:27-30
+        for vec, size, msg in ((q, n, "Linear state cost needs to be a vector of size n"),
+                               (r, m, "Linear control cost needs to be a vector of size n"),
+                               (qf, n, "State terminal linear cost needs to be a vector of size n"),
+                               (x_min, n, "Check the state inequality constraints dimensions"),
+                               (x_max, n, "Check the state inequality constraints dimensions"),
+                               (u_min, m, "Check cotrol iequality constraint dimension"),
+                               (u_max, m, "Check cotrol iequality constraint dimension"),
+                               (du_min, m, "Check cotrol iequality constraint dimension"),
+                               (du_max, m, "Check cotrol iequality constraint dimension")):
+            if not _isempty(vec) and np.asarray(vec).size < size:
+                raise ValueError(msg)
+        if _isempty(u_min) or _isempty(u_max):
+            raise ValueError("Check cotrol iequality constraint dimension")
+        if self.T < 1:
+            raise ValueError("horizon T must be >= 1")
         self._xmin = _vec(x_min) if not _isempty(x_min) else -np.ones(n)
         self._xmax = _vec(x_max) if not _isempty(x_max) else np.ones(n)
         self._umin, self._umax = _vec(u_min), _vec(u_max)
@@ -95,9 +117,14 @@ class FastMPCBatch:
         self.ramp_rows = bool(ramp_rows)
         self.max_batch = int(max_batch)
         self.device = int(device)
+        self._create(s)
+
+    # the three C entry points a subclass (FastMPCMulti) swaps for their multi-device versions
+    def _create(self, s):
         h = C.c_void_p()
-        check(L.fmpc_create(C.byref(h), C.byref(s), self.max_batch, self.device))
+        check(self._L.fmpc_create(C.byref(h), C.byref(s), self.max_batch, self.device))
         self._h = h
+        self._step_fn, self._step_r_fn = self._L.fmpc_step, self._L.fmpc_step_r
 
     def close(self):
         if getattr(self, "_h", None):
@@ -180,7 +207,7 @@ class FastMPCBatch:
         tel = C.c_double(0.0)
         if frontend is None:
             nu0 = self._inst(nu0, NBn, "nu0", nb)
-            check(self._L.fmpc_step(self._h, C.byref(p), nb, _ptr(x0), _ptr(x0_pre), _ptr(u_prev), _ptr(w), _ptr(xf),
+            check(self._step_fn(self._h, C.byref(p), nb, _ptr(x0), _ptr(x0_pre), _ptr(u_prev), _ptr(w), _ptr(xf),
                                     _ptr(X0), _ptr(U0), _ptr(nu0), _ptr(X), _ptr(U), _ptr(status), _ptr(iters),
                                     C.cast(C.byref(tel), C.c_void_p)))
         else:
@@ -220,7 +247,7 @@ class FastMPCBatch:
         status = np.zeros(nb, dtype=np.int32)
         iters = np.zeros(nb, dtype=np.int32)
         tel = C.c_double(0.0)
-        check(self._L.fmpc_step_r(self._h, C.byref(p), nb, 1 if reset else 0, _ptr(x0), _ptr(x0_pre), _ptr(u_prev), _ptr(w),
+        check(self._step_r_fn(self._h, C.byref(p), nb, 1 if reset else 0, _ptr(x0), _ptr(x0_pre), _ptr(u_prev), _ptr(w),
                                   _ptr(xf), _ptr(nu0), _ptr(u0), _ptr(X), _ptr(U), _ptr(status), _ptr(iters),
                                   C.cast(C.byref(tel), C.c_void_p)))
         out = dict(u0=u0, status=status, iters=iters, telapsed=tel.value)
@@ -259,6 +286,72 @@ class FastMPCBatch:
         check(self._L.fmpc_closed_loop(self._h, C.byref(p), nb, K, _ptr(a), _ptr(nu0), _ptr(U_acc), _ptr(X_acc),
                                        _ptr(it), C.cast(C.byref(tel), C.c_void_p)))
         return dict(U_acc=U_acc, X_acc=X_acc, iters=it, telapsed=tel.value)
+
+
+class FastMPCMulti(FastMPCBatch):
+    """Every B200 of the box behind one blocking call (`fmpc_multi_*`): one handle + host thread per device in this process,
+    contiguous shards of ceil(nb / G) instances, no inter-GPU traffic in the solve.  Same `step` / `step_resident` as
+    FastMPCBatch; `stats()` returns the per-device records of the last step (over NCCL if `use_nccl`)."""
+
+    def __init__(self, *args, ngpus=0, devices=None, **kw):
+        self._ngpus_req = int(ngpus)
+        self._devices = None if devices is None else (C.c_int * len(devices))(*devices)
+        if devices is not None:
+            self._ngpus_req = len(devices)
+        super().__init__(*args, **kw)
+
+    def _create(self, s):
+        h = C.c_void_p()
+        check(self._L.fmpc_multi_create(C.byref(h), C.byref(s), self.max_batch, self._ngpus_req,
+                                        None if self._devices is None else C.cast(self._devices, C.c_void_p)))
+        self._h = h
+        self._step_fn, self._step_r_fn = self._L.fmpc_multi_step, self._L.fmpc_multi_step_r
+        self.ngpus = int(self._L.fmpc_multi_ngpus(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fmpc_multi_destroy(self._h)
+            self._h = None
+
+    def _dev_handles(self):
+        return [C.c_void_p(self._L.fmpc_multi_handle(self._h, g)) for g in range(self.ngpus)]
+
+    @property
+    def launch_count(self) -> int:
+        return sum(int(self._L.fmpc_launch_count(h)) for h in self._dev_handles())
+
+    @property
+    def workspace_bytes(self) -> int:
+        return sum(int(self._L.fmpc_workspace_bytes(h)) for h in self._dev_handles())
+
+    @property
+    def kernel_kind(self) -> int:
+        return int(self._L.fmpc_kernel_kind(self._dev_handles()[0]))
+
+    def last_newton_iters(self) -> int:
+        return sum(int(self._L.fmpc_last_newton_iters(h)) for h in self._dev_handles())
+
+    def shard(self, nbatch, g):
+        a, b = C.c_int(0), C.c_int(0)
+        check(self._L.fmpc_multi_shard(self._h, int(nbatch), int(g), C.cast(C.byref(a), C.c_void_p), C.cast(C.byref(b), C.c_void_p)))
+        return a.value, b.value
+
+    def stats(self, use_nccl=False):
+        """Per-device statistics of the last step: list of dict(device, n_solves, device_seconds, newton_iters, status_hist)."""
+        rec = np.zeros((self.ngpus, 8))
+        used = C.c_int(0)
+        nrec = self._L.fmpc_multi_last_stats(self._h, rec.ctypes.data_as(C.c_void_p), 1 if use_nccl else 0,
+                                             C.cast(C.byref(used), C.c_void_p))
+        if nrec < 0:
+            check(nrec)
+        return [dict(device=int(r[0]), n_solves=int(r[1]), device_seconds=float(r[2]), newton_iters=int(r[3]),
+                     status_hist=[int(v) for v in r[4:8]], via_nccl=bool(used.value)) for r in rec[:nrec]]
+
+    def state_update(self, *a, **k):
+        raise NotImplementedError("use a FastMPCBatch for the host-buffer state update; the multi-device handle only solves")
+
+    def closed_loop(self, *a, **k):
+        raise NotImplementedError("fmpc_closed_loop is a single-device entry point; drive the loop with step_resident")
 
 
 # --------------------------------------------------------------------------------------------

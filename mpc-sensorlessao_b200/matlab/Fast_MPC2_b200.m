@@ -5,8 +5,9 @@ classdef Fast_MPC2_b200
     % Same 23-argument constructor, same property names, same solver method names.  README.md:548-570 runs
     % unmodified after  Fast_MPC2 -> Fast_MPC2_b200.  x0 / x0_pre / w / xf / x_init may carry one COLUMN PER
     % INSTANCE (n x nb, ...) to solve a whole batch in one call; the result is then N x nb.
-    % The device handle is cached per problem (A1, A2, B, costs, bounds, T), so constructing the object every
-    % control step, as the reference's closed loop does, costs nothing on the GPU side.
+    % The device handle is cached per problem (every constructor constant, compared with isequal), so constructing the
+    % object every control step, as the reference's closed loop does, costs nothing on the GPU side;
+    % Fast_MPC2_b200.clear_cache() destroys the cached handles.
     properties
         Q; R; S; q; r; Qf; qf; x_min; x_max; u_min; u_max; du_min; du_max; T; x0; x0_pre; u_prev; A1; A2; B; w
         x_final; x_init
@@ -34,7 +35,17 @@ classdef Fast_MPC2_b200
             end
         end
         function x_opt = mpc_fixed_log_newton(obj, nw, k)       % Fast_MPC2.m:124-130
+            if isempty(nw), nw = 1000; end                      % inf_newton_solver.m:4-8: nw = [] => max_iter = 1000
             x_opt = obj.run(0, struct('kappa', k, 'niters', nw), 0, 0);
+        end
+        function [u0, status, iters] = mpc_step_resident(obj, nw, k, reset)
+            % One step of a closed loop whose solver state stays on the GPU (fmpc_step_r): warm start = the previous
+            % call's solution shifted one stage, x0_pre = [] => previous x0, u_prev = [] => previous U(:,0).  Only x0 goes
+            % to the device and only U(:,0) (README.md:589) comes back.  reset = true starts a loop (cold start).
+            if isempty(nw), nw = 1000; end
+            h = obj.handle(size(obj.x0, 2));
+            [u0, status, iters] = fmpc_mex('step_r', h, struct('kappa', k, 'niters', nw), logical(reset), obj.x0, obj.x0_pre, ...
+                                           obj.u_prev, obj.w, obj.x_final, obj.nu0);
         end
         function x_opt = mpc_fixed_log(obj, k)                  % Fast_MPC2.m:116-123
             x_opt = obj.run(1, struct('kappa', k), 0, 0);
@@ -60,19 +71,42 @@ classdef Fast_MPC2_b200
             end
         end
         function h = handle(obj, nb)
-            persistent cache
-            if isempty(cache), cache = containers.Map('KeyType', 'char', 'ValueType', 'any'); end
+            h = Fast_MPC2_b200.cache('get', obj, nb);
+        end
+    end
+    methods (Static)
+        function clear_cache()
+            % destroys every cached device handle (fmpc_destroy); call when the loop is over or before `clear mex`
+            Fast_MPC2_b200.cache('clear', [], 0);
+        end
+        function h = cache(cmd, obj, nb)
+            % Handles are cached per problem.  The key is EVERY constructor constant the handle holds on the GPU (matrices,
+            % linear costs, all bounds, T, flags, batch capacity, device), compared entry by entry with isequal -- never a
+            % checksum, which two different problems can share.
+            persistent entries
+            h = [];
+            if isempty(entries), entries = {}; end
+            if strcmp(cmd, 'clear')
+                for i = 1:numel(entries), fmpc_mex('destroy', entries{i}.h); end
+                entries = {};
+                return
+            end
             [n, m] = size(obj.B);
             sys = struct('n', n, 'm', m, 'T', obj.T, 'var_order', 1 + ~isempty(obj.A2), 'ramp_rows', obj.ramp_rows, ...
                          'var1_literal_bug', obj.var1_literal_bug, ...
                          'A1', obj.A1, 'A2', obj.A2, 'B', obj.B, 'Q', obj.Q, 'R', obj.R, 'Qf', obj.Qf, 'q', obj.q, 'r', obj.r, ...
                          'qf', obj.qf, 'x_min', obj.x_min, 'x_max', obj.x_max, 'u_min', obj.u_min, 'u_max', obj.u_max, ...
                          'du_min', obj.du_min, 'du_max', obj.du_max);
-            key = sprintf('%d_%d_%d_%d_%d_%d_%.17g', n, m, obj.T, max(nb, 1), obj.ramp_rows, obj.var1_literal_bug, ...
-                          sum(obj.A1(:)) + 3*sum(obj.B(:)) + 5*sum(obj.Q(:)) + 7*sum(obj.R(:)) + 11*sum(obj.Qf(:)) + ...
-                          13*sum(obj.u_min) + 17*sum(obj.u_max) + 19*sum(obj.A2(:)) + 23*obj.ramp_rows*(sum(obj.du_min) + 2*sum(obj.du_max)));
-            if ~isKey(cache, key), cache(key) = fmpc_mex('create', sys, max(nb, 1), obj.device); end
-            h = cache(key);
+            key = struct('sys', sys, 'nb', max(nb, 1), 'device', obj.device);
+            for i = 1:numel(entries)
+                if isequal(entries{i}.key, key), h = entries{i}.h; return, end
+            end
+            if numel(entries) >= 8                               % least recently created goes first
+                fmpc_mex('destroy', entries{1}.h);
+                entries(1) = [];
+            end
+            h = fmpc_mex('create', sys, max(nb, 1), obj.device);
+            entries{end + 1} = struct('key', key, 'h', h);
         end
     end
 end

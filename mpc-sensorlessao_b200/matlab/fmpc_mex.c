@@ -7,6 +7,7 @@
  *   h = fmpc_mex('create', sys, max_batch, device)      sys: struct with the fields of fmpc_sys
  *   [z, status, iters, telapsed] = fmpc_mex('step', h, params, x0, x0_pre, u_prev, w, xf, z0, nu0)
  *   [z, status, iters, telapsed] = fmpc_mex('frontend', h, mode, params, kmin, kmax, x0, x0_pre, u_prev, w, xf, z0, nu0)
+ *   [u0, status, iters, telapsed] = fmpc_mex('step_r', h, params, reset, x0, x0_pre, u_prev, w, xf, nu0)     resident closed-loop step
  *   x_next = fmpc_mex('state_update', h, x, x_pre, u, w)
  *   fmpc_mex('destroy', h)
  *   hz = fmpc_mex('zmf_create', nL, N, max_frames, device);  c = fmpc_mex('zmf_fit', hz, frames);  fmpc_mex('zmf_destroy', hz)
@@ -134,6 +135,23 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
             run_solve(nlhs, plhs, h, fe ? (int)mxGetScalar(prhs[2]) : 0, &p,
                       fe ? mxGetScalar(prhs[4]) : 0.0, fe ? mxGetScalar(prhs[5]) : 0.0, a, n, m, T);
         }
+    } else if (!strcmp(cmd, "step_r")) {
+        /* h, params, reset, x0, x0_pre, u_prev, w, xf, nu0  ->  U(:,0) per instance (README.md:589), status, iters, telapsed */
+        fmpc_handle *h = (fmpc_handle *)get_handle(prhs[1]);
+        fmpc_params p;
+        int n = 0, m = 0, T = 0, nb;
+        double te = 0.0;
+        if (nrhs < 10) mexErrMsgIdAndTxt("fmpc:usage", "not enough arguments");
+        read_params(prhs[2], &p);
+        check(fmpc_get_dims(h, &n, &m, &T));
+        nb = (int)mxGetN(prhs[4]);
+        plhs[0] = mxCreateDoubleMatrix((mwSize)m, (mwSize)nb, mxREAL);
+        plhs[1] = mxCreateNumericMatrix(nb, 1, mxINT32_CLASS, mxREAL);
+        plhs[2] = mxCreateNumericMatrix(nb, 1, mxINT32_CLASS, mxREAL);
+        check(fmpc_step_r(h, &p, nb, mxGetScalar(prhs[3]) != 0.0 ? FMPC_R_RESET : 0, opt(prhs[4]), opt(prhs[5]), opt(prhs[6]),
+                          opt(prhs[7]), opt(prhs[8]), opt(prhs[9]), mxGetPr(plhs[0]), NULL, NULL, (int *)mxGetData(plhs[1]),
+                          (int *)mxGetData(plhs[2]), &te));
+        plhs[3] = mxCreateDoubleScalar(te);
     } else if (!strcmp(cmd, "state_update")) {
         const int nb = (int)mxGetN(prhs[2]);
         plhs[0] = mxCreateDoubleMatrix(mxGetM(prhs[2]), nb, mxREAL);

@@ -113,8 +113,8 @@ def test_side_entry_points_validate_before_cuda(pk):
 def test_library_mt19937_is_matlabs_default_stream(tmp_path):
     """nu0 = NULL => rand(length(b),1) (inf_newton_solver.m:2) from MATLAB's default stream MT19937(5489).
     The host seeds the state (struct MT19937 of csrc/fmpc_api.cu, compiled here); the stream itself is generated on the
-    device in three barrier-separated phases per 624-word block (fmpc_mt_fill_kernel) -- restated here in numpy with the
-    kernel's index ranges and compared with numpy's MT19937; the kernel itself is checked by the -m gpu tests."""
+    device, every word of the next 624-word block expressed by words of the current one (mt_next_word in
+    csrc/fmpc_kernels.cu) -- restated here in numpy with the kernel's index ranges and compared with numpy's MT19937; the kernel itself is checked by the -m gpu tests."""
     import subprocess
     src = open(os.path.join(ROOT, "mpc-sensorlessao_b200", "csrc", "fmpc_api.cu")).read()
     a = src.index("struct MT19937 {")
@@ -138,13 +138,16 @@ def test_library_mt19937_is_matlabs_default_stream(tmp_path):
 
     o, out = seed_state.copy(), []
     for _ in range(7):                                  # 7 blocks = 2184 doubles
-        w = np.zeros(624, dtype=np.uint32)
-        t = np.arange(227)
-        w[t] = o[t + 397] ^ twist(o[t], o[t + 1])                       # phase 1: tid < 227
-        w[t + 227] = w[t] ^ twist(o[t + 227], o[t + 228])               # phase 2
-        t = np.arange(169)
-        w[t + 454] = w[t + 227] ^ twist(o[t + 454], o[t + 455])         # phase 3: tid < 169 ...
-        w[623] = w[396] ^ twist(o[623:624], w[0:1])[0]                  # ... and tid == 169
+        w = np.zeros(624, dtype=np.uint32)              # mt_next_word: every word of the next block from the current one
+        e = np.arange(0, 227)
+        w[e] = o[e + 397] ^ twist(o[e], o[e + 1])
+        e = np.arange(227, 454)
+        w[e] = o[e + 170] ^ twist(o[e - 227], o[e - 226]) ^ twist(o[e], o[e + 1])
+        e = np.arange(454, 623)
+        w[e] = o[e - 57] ^ twist(o[e - 454], o[e - 453]) ^ twist(o[e - 227], o[e - 226]) ^ twist(o[e], o[e + 1])
+        n0 = o[397:398] ^ twist(o[0:1], o[1:2])
+        n396 = o[566:567] ^ twist(o[169:170], o[170:171]) ^ twist(o[396:397], o[397:398])
+        w[623] = (n396 ^ twist(o[623:624], n0))[0]
         y = temper(w)
         out.append(((y[0::2] >> np.uint32(5)).astype(np.float64) * 67108864.0 + (y[1::2] >> np.uint32(6)).astype(np.float64))
                    * (1.0 / 9007199254740992.0))
