@@ -346,9 +346,13 @@ def measure_loop(cx, name, p, nb, K, W, hostlegs=True):
     dit = torch.zeros((K + 1, nb), dtype=torch.int32, device=dev)
     stream = torch.cuda.Stream(dev)
 
+    # dual starts of the value leg: resident in HBM like every other input (NSETS rotating arrays); the host legs below use
+    # nu0 = NULL instead, i.e. the handle's MATLAB stream generated on the device (nothing to ship)
+    dnu = torch.rand((NSETS, nb, T * n), dtype=torch.float64, device=dev)
+
     def step_dev(k, slot):
-        rc = L.fmpc_step_r_d(hb._h, C.byref(params), nb, 1 if k == 0 else 0, vp(dx0[k]), None, None, None, None, None, vp(du0),
-                             None, None, vp(dst[slot]), vp(dit[slot]), C.c_void_p(stream.cuda_stream))
+        rc = L.fmpc_step_r_d(hb._h, C.byref(params), nb, 1 if k == 0 else 0, vp(dx0[k]), None, None, None, None, vp(dnu[k % NSETS]),
+                             vp(du0), None, None, vp(dst[slot]), vp(dit[slot]), C.c_void_p(stream.cuda_stream))
         if rc:
             raise pk.FmpcError(rc, pk.strerror(rc))
 

@@ -179,6 +179,7 @@ struct fmpc_handle {
     cudaStream_t s_gen = nullptr;
     cudaEvent_t ev_nu_ready[2] = {}, ev_nu_free[2] = {};
     bool nu_free_pending[2] = {false, false};
+    bool nu_stream_active = false;        // the last call drew its dual starts from the stream (and prefetched the next ones)
     // staging of pageable host buffers (fmpc_step): NSTAGE pinned slots per direction, worker threads created on first use
     static constexpr int NSTAGE = 3;
     PinBuf stg_in[NSTAGE], stg_out[NSTAGE];
@@ -611,6 +612,7 @@ static int nu_take(fmpc_handle *h, size_t need, cudaStream_t consumer, const dou
     }
     h->nu_cur = oth;
     h->nu_have = have;
+    h->nu_stream_active = true;
     return FMPC_OK;
 }
 static int nu_release(fmpc_handle *h, int which, cudaStream_t consumer)
@@ -639,6 +641,10 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
     SolveLaunchCfg cfg = h->cfg;
     if (by_smid) A.slot_base = -1;                              // `part` only selects the counter block
     else if (nparts > 1) { cfg.grid = h->cfg.grid / nparts; A.slot_base = part * cfg.grid; }
+    // While the handle's MATLAB stream is in use its generator (one CTA, fmpc_mt_fill_kernel) runs one call ahead, underneath
+    // this solve.  The persistent solve kernels fill every SM, and a generator CTA that does not fit beside one of their CTAs
+    // would wait for the whole solve (and the NEXT solve for it): leave it one SM.
+    if (h->nu_stream_active && nparts == 1 && !by_smid && cfg.grid > 1 && (h->cfg.use_mma == 2 || h->cfg.use_mma == 1)) cfg.grid -= 1;
     A.ws = h->ws.as<double>(); A.ws_stride = h->ws_stride;
     A.prof = (long long *)(h->counters.as<char>() + 64);
     CU_OK(cudaMemsetAsync(cblk, 0, keep_totals ? 4 : 256, st));     // instance counter [+ iteration total, phase counters]
@@ -651,7 +657,7 @@ static int step_device(fmpc_handle *h, const fmpc_params *p, int nbatch, const d
         if (nbatch > h->max_batch) return FMPC_ERR_BATCH;     // its scratch is sized by max_batch
         fmpc_launch_solve_gen(h->S, h->G, A, h->cfg, st);
     } else if (h->cfg.use_mma == 2) fmpc_launch_solve_warp(h->S, A, cfg, st);
-    else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, h->cfg, st);
+    else if (h->cfg.use_mma == 1) fmpc_launch_solve_mma(h->S, A, cfg, st);
     else fmpc_launch_solve(h->S, A, h->cfg, st);
     CU_OK(cudaGetLastError());
     h->launches += 1;
@@ -729,6 +735,7 @@ int fmpc_step(fmpc_handle *h, const fmpc_params *p, int nbatch, const double *x0
     while (nch > 1 && (size_t)(nch - 1) * per >= nb) --nch;           // no empty trailing chunk
     if (smid_mode) CU_OK(cudaMemsetAsync(h->counters.p, 0, 256 * fmpc_handle::MAX_CHUNKS, si));   // every chunk's counter block, ahead of all chunks
     if (!nu0) { rc = nu_take(h, nb * NBn, si, &nu_dev, &nu_which); if (rc) return rc; }
+    else h->nu_stream_active = false;
     // the per-instance vectors are small: one copy each for the whole batch, ahead of the chunked arrays
     CU_OK(cudaMemcpyAsync(h->d_x0.p, x0, nb * n * 8, cudaMemcpyHostToDevice, si));
     if (x0_pre) CU_OK(cudaMemcpyAsync(h->d_x0pre.p, x0_pre, nb * n * 8, cudaMemcpyHostToDevice, si));
@@ -874,6 +881,7 @@ static int step_resident(fmpc_handle *h, const fmpc_params *p, int nbatch, int f
     const double *nu_dev = nullptr;
     int nu_which = -1;
     if (nu0) {
+        h->nu_stream_active = false;
         CU_OK(cudaMemcpyAsync(h->d_nu0.p, nu0, nb * NBn * 8, cudaMemcpyDefault, st));
         nu_dev = h->d_nu0.as<double>();
     } else {
@@ -1083,7 +1091,7 @@ int fmpc_closed_loop(fmpc_handle *h, const fmpc_params *p, int nbatch, int K, co
         CU_OK(cudaEventRecord(h->ev_in[buf], si));
         return FMPC_OK;
     };
-    if (nu0) { rc = upload_nu(0); if (rc) return rc; }
+    if (nu0) { h->nu_stream_active = false; rc = upload_nu(0); if (rc) return rc; }
     for (int k = 0; k < K; ++k) {
         const int buf = k & 1;
         // x0 = a[:,k,b] + B u_prev ; x0_pre <- previous x0 ; warm start shifted one stage

@@ -9,6 +9,7 @@
 // L2-resident scratch area (grid-sized, not batch-sized).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include "fmpc_internal.h"
 #include "fmpc_device.cuh"
 
@@ -455,17 +456,21 @@ __device__ __forceinline__ unsigned mt_next_word(const unsigned *o, const int e)
     const unsigned n396 = o[566] ^ mt_f(o[169], o[170]) ^ mt_f(o[396], o[397]);
     return n396 ^ mt_f(o[623], n0);
 }
-__global__ void __launch_bounds__(256, 1) fmpc_mt_fill_kernel(unsigned *__restrict__ state, double *__restrict__ out,
-                                                              unsigned long long count)
+// The first MT_TWIST threads form the next block, the others temper and store the current one; both only read the current
+// block, so ONE CTA barrier per block hands it over.
+template <int MT_THREADS, int MT_TWIST>
+__global__ void __launch_bounds__(MT_THREADS, 1) fmpc_mt_fill_kernel(unsigned *__restrict__ state, double *__restrict__ out,
+                                                                     unsigned long long count)
 {
+    constexpr int MT_OUT = MT_THREADS - MT_TWIST, NTW = (624 + MT_TWIST - 1) / MT_TWIST, NOUT = (312 + MT_OUT - 1) / MT_OUT;
     __shared__ __align__(16) unsigned mt[2][624];
     const int tid = threadIdx.x;
-    for (int i = tid; i < 624; i += 256) mt[0][i] = state[i];
+    for (int i = tid; i < 624; i += MT_THREADS) mt[0][i] = state[i];
     int idx = (int)state[624], cur = 0;
     unsigned long long done = 0;
     __syncthreads();
     if (idx >= 624 && count > 0) {          // nothing unread in the stored block: form the first one
-        for (int e = tid; e < 624; e += 256) mt[1][e] = mt_next_word(mt[0], e);
+        for (int e = tid; e < 624; e += MT_THREADS) mt[1][e] = mt_next_word(mt[0], e);
         __syncthreads();
         cur = 1; idx = 0;
     }
@@ -476,18 +481,27 @@ __global__ void __launch_bounds__(256, 1) fmpc_mt_fill_kernel(unsigned *__restri
         const int take = (left < (unsigned long long)avail) ? (int)left : avail;
         const bool more = left > (unsigned long long)avail;          // another block is needed after this one
         const unsigned *o = mt[cur];
-        if (more) {
-            unsigned *w = mt[cur ^ 1];
-            for (int e = tid; e < 624; e += 256) w[e] = mt_next_word(o, e);
-        }
-        if (out) {
-            for (int t = tid; t < take; t += 256) {
-                const uint2 y = *reinterpret_cast<const uint2 *>(o + idx + 2 * t);      // idx is even: 8-byte aligned
-                const unsigned a = mt_temper(y.x) >> 5, b = mt_temper(y.y) >> 6;
-                // (a 2^26 + b) 2^-53 without integer -> double conversions: both pieces are exact in the mantissa of 2^52 + v
-                const double da = __longlong_as_double(0x4330000000000000ll | (long long)a) - 4503599627370496.0;
-                const double db = __longlong_as_double(0x4330000000000000ll | (long long)b) - 4503599627370496.0;
-                out[done + t] = (da * 67108864.0 + db) * (1.0 / 9007199254740992.0);
+        if (tid < MT_TWIST) {
+            if (more) {
+                unsigned *w = mt[cur ^ 1];
+                unsigned v[NTW];
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) { const int e = tid + MT_TWIST * j; if (e < 624) v[j] = mt_next_word(o, e); }
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) { const int e = tid + MT_TWIST * j; if (e < 624) w[e] = v[j]; }
+            }
+        } else if (out) {
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+                const int t = tid - MT_TWIST + MT_OUT * j;
+                if (t < take) {
+                    const uint2 y = *reinterpret_cast<const uint2 *>(o + idx + 2 * t);      // idx is even: 8-byte aligned
+                    const unsigned a = mt_temper(y.x) >> 5, b = mt_temper(y.y) >> 6;
+                    // (a 2^26 + b) 2^-53 without integer -> double conversions: both pieces are exact in the mantissa of 2^52 + v
+                    const double da = __longlong_as_double(0x4330000000000000ll | (long long)a) - 4503599627370496.0;
+                    const double db = __longlong_as_double(0x4330000000000000ll | (long long)b) - 4503599627370496.0;
+                    out[done + t] = (da * 67108864.0 + db) * (1.0 / 9007199254740992.0);
+                }
             }
         }
         __syncthreads();
@@ -495,7 +509,7 @@ __global__ void __launch_bounds__(256, 1) fmpc_mt_fill_kernel(unsigned *__restri
         done += take;
         if (more) { cur ^= 1; idx = 0; }
     }
-    for (int i = tid; i < 624; i += 256) state[i] = mt[cur][i];
+    for (int i = tid; i < 624; i += MT_THREADS) state[i] = mt[cur][i];
     if (tid == 0) state[624] = (unsigned)idx;
 }
 
@@ -564,7 +578,11 @@ void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const d
 
 void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count, void *stream)
 {
-    fmpc_mt_fill_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, out, count);
+    // 8 warps form the next block, 4 store the current one: the fastest split measured (scripts/ubench/mt.cu,
+    // profiles/r02_mt_generator.log); a block costs ~500-700 cycles whatever the split -- one LDS -> ALU -> STS -> barrier
+    // round trip per 624 words is the floor of a single dependency chain
+    fmpc_mt_fill_kernel<384, 256><<<1, 384, 0, (cudaStream_t)stream>>>(state, out, count);
+}
 }
 
 void fmpc_launch_shift_inplace(int n, int m, int T, int nbatch, double *X, double *U, void *stream)
