@@ -279,6 +279,11 @@ typedef struct zmf_handle zmf_handle;
  * n = 0..N, m = -n:2:n) and its least-squares operator W = pinv(Z) in fp64 on the host, and
  * uploads W scattered to the full nL x nL frame (zeros outside the pupil). */
 int zmf_create(zmf_handle **out, int nL, int N, int max_frames, int device);
+/* zernmodfit on an ARBITRARY sample set (zernmodfit.m:154-213 takes any vectors r, theta, data): the basis is evaluated at
+ * the npts given samples (0 <= r <= 1 else FMPC_ERR_DIM, zernmodfit.m:182-184), W = pinv(Z) once; zmf_fit then takes
+ * `frames` = npts x nf (one data vector per column, in the order of r / theta) and returns coef nmodes x nf.
+ * FMPC_ERR_NOT_PD if the samples do not determine the modes (Z rank deficient); zmf_synth is not available. */
+int zmf_create_samples(zmf_handle **out, int npts, const double *r, const double *theta, int N, int max_frames, int device);
 void zmf_destroy(zmf_handle *h);
 int zmf_nmodes(const zmf_handle *h);
 int zmf_npix_in(const zmf_handle *h);
@@ -301,7 +306,7 @@ long long zmf_launch_count(const zmf_handle *h);
 /* with A_s (npix x nmodes, column-major; the caller removes the piston column like           */
 /* README.md:289-290) and b_s (npix) from model_approx.mat.  Batched: y is npix x nb (one      */
 /* measurement vector Y_M per column), x_hat is nmodes x nb.  b_s may be NULL (zeros).         */
-/* FMPC_ERR_NOT_PD if A_s is rank deficient (lsqminnorm's minimum-norm branch is not covered). */
+/* Rank-deficient A_s: the minimum-norm solution, like lsqminnorm (eigenvalues of A_s'A_s below max(size) * eps(norm) dropped). */
 typedef struct zmf_handle est_handle;
 int est_create(est_handle **out, int npix, int nmodes, const double *A_s, const double *b_s, int max_batch, int device);
 void est_destroy(est_handle *h);

@@ -11,9 +11,9 @@ All compute runs in the CUDA library `lib/libfmpc_b200.so`; there is no CPU fall
 from ._lib import (FmpcError, FmpcParams, build_library, device_count, fp64_peak, lib_path, load_library,
                    strerror)
 from .fast_mpc2 import FastMPCBatch, FastMPCMulti, Fast_MPC2, Fast_MPC2_VAR1, deinterleave, interleave
-from .zernike import ZernikeFitter, zernmodfit
+from .zernike import SampleFitter, ZernikeFitter, zernmodfit
 from .estimator import Estimator, identify_var
 
 __all__ = ["FmpcError", "FmpcParams", "build_library", "device_count", "fp64_peak", "lib_path", "load_library",
            "strerror", "FastMPCBatch", "FastMPCMulti", "Fast_MPC2", "Fast_MPC2_VAR1", "deinterleave", "interleave",
-           "ZernikeFitter", "zernmodfit", "Estimator", "identify_var"]
+           "ZernikeFitter", "SampleFitter", "zernmodfit", "Estimator", "identify_var"]

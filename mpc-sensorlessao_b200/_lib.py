@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "fmpc_step_r", "fmpc_step_r_d", "fmpc_step_z", "fmpc_frontend", "fmpc_frontend_nouter", "fmpc_state_update", "fmpc_state_update_d",
     "fmpc_closed_loop", "fmpc_get_dims", "fmpc_workspace_bytes", "fmpc_launch_count", "fmpc_last_newton_iters", "fmpc_kernel_kind", "fmpc_last_profile", "fmpc_strerror",
     "fmpc_fp64_peak", "fmpc_seed_stream", "fmpc_multi_create", "fmpc_multi_destroy", "fmpc_multi_ngpus", "fmpc_multi_shard",
-    "fmpc_multi_handle", "fmpc_multi_step", "fmpc_multi_step_r", "fmpc_multi_last_stats", "zmf_create", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
+    "fmpc_multi_handle", "fmpc_multi_step", "fmpc_multi_step_r", "fmpc_multi_last_stats", "zmf_create", "zmf_create_samples", "zmf_destroy", "zmf_nmodes", "zmf_npix_in", "zmf_fit", "zmf_fit_d", "zmf_synth", "zmf_synth_d",
     "zmf_get_basis", "zmf_get_mask", "zmf_launch_count",
     "est_create", "est_destroy", "est_apply", "est_apply_d", "est_launch_count", "var_identify",
 ]
@@ -122,6 +122,7 @@ def load_library():
     L.fmpc_fp64_peak.argtypes = [C.c_int, C.c_int, C.c_int]
     L.fmpc_fp64_peak.restype = C.c_double
     L.zmf_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.zmf_create_samples.argtypes = [C.POINTER(vp), C.c_int, vp, vp, C.c_int, C.c_int, C.c_int]
     L.zmf_destroy.argtypes = [vp]
     L.zmf_destroy.restype = None
     L.zmf_nmodes.argtypes = [vp]

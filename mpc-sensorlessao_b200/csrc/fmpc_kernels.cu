@@ -583,7 +583,6 @@ void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count,
     // round trip per 624 words is the floor of a single dependency chain
     fmpc_mt_fill_kernel<384, 256><<<1, 384, 0, (cudaStream_t)stream>>>(state, out, count);
 }
-}
 
 void fmpc_launch_shift_inplace(int n, int m, int T, int nbatch, double *X, double *U, void *stream)
 {

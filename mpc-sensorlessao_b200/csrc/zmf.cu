@@ -481,6 +481,97 @@ cudaError_t zmf_launch_synth(const zmf_handle *h, int nframes, const double *coe
 
 // Uploads the least-squares operator W (nmodes x npix, row j contiguous over pixels, exact zeros where mask == 0) and
 // builds the DMMA tables; allocates staging for max_frames.  Shared by zmf_create and est_create.
+// W (M x ldw, row j contiguous over samples; sample p lands in column pidx[p], or p if pidx == NULL) such that W y is the
+// least-squares solution of Z c = y, Z = P x M column-major:  W = inv(Z'Z) Z' by a Cholesky of the Gram matrix in extended
+// precision.  If the Gram matrix is numerically rank deficient: FMPC_ERR_NOT_PD, unless `minnorm`, in which case
+// W = pinv(Z'Z) Z' -- what lsqminnorm(Z'Z, Z'y) returns (README.md:478): eigen-decomposition of the Gram matrix (cyclic
+// Jacobi, extended precision), eigenvalues below lsqminnorm's default tolerance max(size) * eps(norm) dropped.
+// `off` (if given) receives W b for the estimator's constant term.
+static int lsq_operator(const std::vector<double> &Z, int P, int M, const int *pidx, size_t ldw, bool minnorm, const double *b,
+                        std::vector<double> &W, std::vector<double> *off)
+{
+    std::vector<long double> G((size_t)M * M, 0.0L);
+    for (int a = 0; a < M; ++a)
+        for (int c = a; c < M; ++c) {
+            long double sacc = 0.0L;
+            const double *za = &Z[(size_t)a * P], *zc = &Z[(size_t)c * P];
+            for (int p = 0; p < P; ++p) sacc += (long double)za[p] * zc[p];
+            G[(size_t)a * M + c] = G[(size_t)c * M + a] = sacc;
+        }
+    std::vector<long double> Gi;                // pinv of the Gram matrix, only in the minimum-norm branch
+    std::vector<long double> L = G;
+    bool pd = true;
+    for (int j = 0; j < M && pd; ++j) {         // in-place lower Cholesky, row-major
+        const long double g0 = G[(size_t)j * M + j];
+        long double d = L[(size_t)j * M + j];
+        for (int k = 0; k < j; ++k) d -= L[(size_t)j * M + k] * L[(size_t)j * M + k];
+        if (!(d > 1e-13L * g0) || !(g0 > 0.0L)) { pd = false; break; }
+        d = sqrtl(d);
+        L[(size_t)j * M + j] = d;
+        for (int i = j + 1; i < M; ++i) {
+            long double sacc = L[(size_t)i * M + j];
+            for (int k = 0; k < j; ++k) sacc -= L[(size_t)i * M + k] * L[(size_t)j * M + k];
+            L[(size_t)i * M + j] = sacc / d;
+        }
+    }
+    if (!pd) {
+        if (!minnorm) return FMPC_ERR_NOT_PD;
+        std::vector<long double> A = G, V((size_t)M * M, 0.0L);
+        for (int i = 0; i < M; ++i) V[(size_t)i * M + i] = 1.0L;
+        for (int sweep = 0; sweep < 60; ++sweep) {
+            long double offn = 0.0L, dn = 0.0L;
+            for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) (i == j ? dn : offn) += A[(size_t)i * M + j] * A[(size_t)i * M + j];
+            if (offn <= 1e-38L * dn) break;
+            for (int pp = 0; pp < M - 1; ++pp)
+                for (int q = pp + 1; q < M; ++q) {
+                    const long double apq = A[(size_t)pp * M + q];
+                    if (apq == 0.0L) continue;
+                    const long double th = (A[(size_t)q * M + q] - A[(size_t)pp * M + pp]) / (2.0L * apq);
+                    const long double t = (th >= 0 ? 1.0L : -1.0L) / (fabsl(th) + sqrtl(th * th + 1.0L));
+                    const long double c = 1.0L / sqrtl(t * t + 1.0L), sn = t * c;
+                    for (int k = 0; k < M; ++k) {
+                        const long double akp = A[(size_t)k * M + pp], akq = A[(size_t)k * M + q];
+                        A[(size_t)k * M + pp] = c * akp - sn * akq; A[(size_t)k * M + q] = sn * akp + c * akq;
+                    }
+                    for (int k = 0; k < M; ++k) {
+                        const long double apk = A[(size_t)pp * M + k], aqk = A[(size_t)q * M + k];
+                        A[(size_t)pp * M + k] = c * apk - sn * aqk; A[(size_t)q * M + k] = sn * apk + c * aqk;
+                    }
+                    for (int k = 0; k < M; ++k) {
+                        const long double vkp = V[(size_t)k * M + pp], vkq = V[(size_t)k * M + q];
+                        V[(size_t)k * M + pp] = c * vkp - sn * vkq; V[(size_t)k * M + q] = sn * vkp + c * vkq;
+                    }
+                }
+        }
+        long double lmax = 0.0L;
+        for (int i = 0; i < M; ++i) lmax = fmaxl(lmax, fabsl(A[(size_t)i * M + i]));
+        const long double tol = (long double)M * 2.220446049250313e-16L * lmax;       // max(size(G)) * eps(norm(G))
+        Gi.assign((size_t)M * M, 0.0L);
+        for (int e = 0; e < M; ++e) {
+            const long double lam = A[(size_t)e * M + e];
+            if (!(lam > tol)) continue;
+            for (int i = 0; i < M; ++i)
+                for (int j = 0; j < M; ++j) Gi[(size_t)i * M + j] += V[(size_t)i * M + e] * V[(size_t)j * M + e] / lam;
+        }
+    }
+    W.assign((size_t)M * ldw, 0.0);
+    std::vector<long double> col(M), res(M), offl(M, 0.0L);
+    for (int p = 0; p < P; ++p) {       // column p of W: solve (Z'Z) w = Z(p,:)'
+        for (int j = 0; j < M; ++j) col[j] = Z[(size_t)j * P + p];
+        if (pd) {
+            for (int j = 0; j < M; ++j) { long double sacc = col[j]; for (int k = 0; k < j; ++k) sacc -= L[(size_t)j * M + k] * col[k]; col[j] = sacc / L[(size_t)j * M + j]; }
+            for (int j = M - 1; j >= 0; --j) { long double sacc = col[j]; for (int k = j + 1; k < M; ++k) sacc -= L[(size_t)k * M + j] * col[k]; col[j] = sacc / L[(size_t)j * M + j]; }
+            res = col;
+        } else {
+            for (int j = 0; j < M; ++j) { long double sacc = 0.0L; for (int k = 0; k < M; ++k) sacc += Gi[(size_t)j * M + k] * col[k]; res[j] = sacc; }
+        }
+        const size_t cidx = pidx ? (size_t)pidx[p] : (size_t)p;
+        for (int j = 0; j < M; ++j) { W[(size_t)j * ldw + cidx] = (double)res[j]; if (b) offl[j] += res[j] * (long double)b[p]; }
+    }
+    if (off) { off->assign(M, 0.0); for (int j = 0; j < M; ++j) (*off)[j] = (double)offl[j]; }
+    return FMPC_OK;
+}
+
 static bool linfit_upload(zmf_handle *h, const std::vector<double> &W, int sm_count, int max_frames)
 {
     const int M = h->nmodes;
@@ -562,37 +653,45 @@ int zmf_create(zmf_handle **out, int nL, int N, int max_frames, int device)
     h->Z.assign((size_t)P * M, 0.0);
     for (int j = 0; j < M; ++j)
         for (int p = 0; p < P; ++p) h->Z[(size_t)j * P + p] = zern_eval(nn[j], mm[j], rr[p], tt[p]);
-    // W = inv(Z'Z) Z'  via Cholesky of the Gram matrix (long double accumulation)
-    std::vector<long double> G((size_t)M * M, 0.0L);
-    for (int a = 0; a < M; ++a)
-        for (int b = a; b < M; ++b) {
-            long double s = 0.0L;
-            const double *za = &h->Z[(size_t)a * P], *zb = &h->Z[(size_t)b * P];
-            for (int p = 0; p < P; ++p) s += (long double)za[p] * zb[p];
-            G[(size_t)a * M + b] = G[(size_t)b * M + a] = s;
-        }
-    for (int j = 0; j < M; ++j) {       // in-place lower Cholesky, row-major G[r*M+c]
-        long double d = G[(size_t)j * M + j];
-        for (int k = 0; k < j; ++k) d -= G[(size_t)j * M + k] * G[(size_t)j * M + k];
-        if (!(d > 0.0L)) { delete h; return FMPC_ERR_NOT_PD; }
-        d = sqrtl(d);
-        G[(size_t)j * M + j] = d;
-        for (int i = j + 1; i < M; ++i) {
-            long double s = G[(size_t)i * M + j];
-            for (int k = 0; k < j; ++k) s -= G[(size_t)i * M + k] * G[(size_t)j * M + k];
-            G[(size_t)i * M + j] = s / d;
-        }
-    }
-    std::vector<double> W((size_t)M * h->npix, 0.0);
-    std::vector<long double> col(M);
-    for (int p = 0; p < P; ++p) {       // solve G w = Z(p,:)'
-        for (int j = 0; j < M; ++j) col[j] = h->Z[(size_t)j * P + p];
-        for (int j = 0; j < M; ++j) { long double s = col[j]; for (int k = 0; k < j; ++k) s -= G[(size_t)j * M + k] * col[k]; col[j] = s / G[(size_t)j * M + j]; }
-        for (int j = M - 1; j >= 0; --j) { long double s = col[j]; for (int k = j + 1; k < M; ++k) s -= G[(size_t)k * M + j] * col[k]; col[j] = s / G[(size_t)j * M + j]; }
-        for (int j = 0; j < M; ++j) W[(size_t)j * h->npix + pidx[p]] = (double)col[j];
+    std::vector<double> W;
+    {
+        const int rcw = lsq_operator(h->Z, P, M, pidx.data(), (size_t)h->npix, false, nullptr, W, nullptr);
+        if (rcw) { delete h; return rcw; }
     }
     const bool ok = linfit_upload(h, W, prop.multiProcessorCount, max_frames);
     if (!ok) { zmf_destroy(h); return FMPC_ERR_CUDA; }
+    *out = h;
+    return FMPC_OK;
+}
+
+int zmf_create_samples(zmf_handle **out, int npts, const double *r, const double *theta, int N, int max_frames, int device)
+{
+    if (!out) return FMPC_ERR_NULL;
+    *out = nullptr;
+    if (!r || !theta) return FMPC_ERR_NULL;
+    if (npts < 1 || npts > (1 << 26) || N < 0 || N > 40 || max_frames < 1) return FMPC_ERR_DIM;
+    for (int p = 0; p < npts; ++p) if (!(r[p] >= 0.0 && r[p] <= 1.0)) return FMPC_ERR_DIM;       // zernmodfit.m:182-184
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) return FMPC_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return FMPC_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return FMPC_ERR_CUDA;
+    zmf_handle *h = new (std::nothrow) zmf_handle();
+    if (!h) return FMPC_ERR_CUDA;
+    h->device = device; h->nL = 0; h->N = N; h->npix = npts; h->npix_in = npts;
+    h->nmodes = (N + 1) * (N + 2) / 2;
+    h->mask.assign(npts, 1);
+    const int P = npts, M = h->nmodes;
+    if (P < M) { delete h; return FMPC_ERR_DIM; }
+    h->Z.assign((size_t)P * M, 0.0);
+    int j = 0;
+    for (int x = 0; x <= N; ++x)
+        for (int m = -x; m <= x; m += 2, ++j)                      // zernmodfit.m:195-198
+            for (int p = 0; p < P; ++p) h->Z[(size_t)j * P + p] = zern_eval(x, m, r[p], theta[p]);
+    std::vector<double> W;
+    const int rcw = lsq_operator(h->Z, P, M, nullptr, (size_t)P, false, nullptr, W, nullptr);
+    if (rcw) { delete h; return rcw; }
+    if (!linfit_upload(h, W, prop.multiProcessorCount, max_frames)) { zmf_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
     return FMPC_OK;
 }
@@ -843,39 +942,14 @@ int est_create(est_handle **out, int npix, int nmodes, const double *A_s, const 
     h->mask.assign(npix, 1);
     const int P = npix, M = nmodes;
     h->Z.assign(A_s, A_s + (size_t)P * M);                 // column-major npix x nmodes, like the Zernike basis
-    std::vector<long double> G((size_t)M * M, 0.0L);
-    for (int a = 0; a < M; ++a)
-        for (int b = a; b < M; ++b) {
-            long double sacc = 0.0L;
-            const double *za = &h->Z[(size_t)a * P], *zb = &h->Z[(size_t)b * P];
-            for (int p = 0; p < P; ++p) sacc += (long double)za[p] * zb[p];
-            G[(size_t)a * M + b] = G[(size_t)b * M + a] = sacc;
-        }
-    for (int j = 0; j < M; ++j) {
-        const long double g0 = G[(size_t)j * M + j];
-        long double d = g0;
-        for (int k = 0; k < j; ++k) d -= G[(size_t)j * M + k] * G[(size_t)j * M + k];
-        // (numerically) rank-deficient A_s: lsqminnorm would switch to its minimum-norm branch, which is not covered
-        if (!(d > 1e-13L * g0)) { delete h; return FMPC_ERR_NOT_PD; }
-        d = sqrtl(d);
-        G[(size_t)j * M + j] = d;
-        for (int i = j + 1; i < M; ++i) {
-            long double sacc = G[(size_t)i * M + j];
-            for (int k = 0; k < j; ++k) sacc -= G[(size_t)i * M + k] * G[(size_t)j * M + k];
-            G[(size_t)i * M + j] = sacc / d;
-        }
-    }
-    std::vector<double> W((size_t)M * P, 0.0), off(M, 0.0);
-    std::vector<long double> col(M), offl(M, 0.0L);
-    for (int p = 0; p < P; ++p) {
-        for (int j = 0; j < M; ++j) col[j] = h->Z[(size_t)j * P + p];
-        for (int j = 0; j < M; ++j) { long double sacc = col[j]; for (int k = 0; k < j; ++k) sacc -= G[(size_t)j * M + k] * col[k]; col[j] = sacc / G[(size_t)j * M + j]; }
-        for (int j = M - 1; j >= 0; --j) { long double sacc = col[j]; for (int k = j + 1; k < M; ++k) sacc -= G[(size_t)k * M + j] * col[k]; col[j] = sacc / G[(size_t)j * M + j]; }
-        for (int j = 0; j < M; ++j) { W[(size_t)j * P + p] = (double)col[j]; if (b_s) offl[j] += col[j] * (long double)b_s[p]; }
+    // rank-deficient A_s: lsqminnorm's minimum-norm branch (README.md:478)
+    std::vector<double> W, off;
+    {
+        const int rcw = lsq_operator(h->Z, P, M, nullptr, (size_t)P, true, b_s, W, &off);
+        if (rcw) { delete h; return rcw; }
     }
     bool ok = linfit_upload(h, W, prop.multiProcessorCount, max_batch);
     if (ok && b_s) {
-        for (int j = 0; j < M; ++j) off[j] = (double)offl[j];
         ok = cudaMalloc(&h->d_off, (size_t)M * 8) == cudaSuccess && cudaMemcpy(h->d_off, off.data(), (size_t)M * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) { zmf_destroy(h); return FMPC_ERR_CUDA; }

@@ -3,9 +3,10 @@
   zernmodfit(r, theta, data, N)  <->  zernmodfit.m:1  (same arguments; returns (ad, nm))
   ZernikeFitter(nL, N)           :   the driver loop README.md:78-93 batched over frames
 
-The GPU path is defined on the driver's fixed pupil grid (README.md:78-84): `zernmodfit`
-checks that (r, theta) ARE that grid (they are in every call the reference makes) and raises
-otherwise -- there is no CPU fallback for arbitrary sample sets.
+  SampleFitter(r, theta, N)      :   the same fit for an ARBITRARY sample set (zernmodfit.m:154-213 takes any vectors)
+
+`zernmodfit` uses the frame kernel when (r, theta) is the driver's fixed pupil grid (README.md:78-84, every call the
+reference makes) and a `SampleFitter` otherwise; all arithmetic runs on the GPU, there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -90,7 +91,68 @@ class ZernikeFitter:
         return np.ascontiguousarray(np.transpose(out, (0, 2, 1))), tel.value
 
 
+class SampleFitter:
+    """zernmodfit for an arbitrary sample set (r, theta): the basis and its least-squares operator are built once
+    (`zmf_create_samples`), `fit(data)` projects any number of data vectors sampled at those points."""
+
+    def __init__(self, r, theta, N: int, max_frames: int = 64, device: int = 0):
+        self._L = load_library()
+        self._r = np.ascontiguousarray(np.asarray(r, dtype=np.float64).reshape(-1))
+        self._th = np.ascontiguousarray(np.asarray(theta, dtype=np.float64).reshape(-1))
+        if self._r.shape != self._th.shape:
+            raise ValueError("The inputs R, THETA, and DATA must all have the same number of elements.")
+        if np.any((self._r > 1) | (self._r < 0)):
+            raise ValueError("All R must be between 0 and 1.")                                           # zernmodfit.m:182-184
+        self.N, self.npts = int(N), int(self._r.shape[0])
+        h = C.c_void_p()
+        check(self._L.zmf_create_samples(C.byref(h), self.npts, _ptr(self._r), _ptr(self._th), self.N, int(max_frames), int(device)))
+        self._h = h
+        self.nmodes = int(self._L.zmf_nmodes(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.zmf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def fit(self, data: np.ndarray):
+        """data: (nf, npts) or (npts,) -> (coef (nf, nmodes), telapsed seconds)."""
+        data = np.ascontiguousarray(np.asarray(data, dtype=np.float64))
+        if data.ndim == 1:
+            data = data.reshape(1, -1)
+        if data.shape[1] != self.npts:
+            raise ValueError("The inputs R, THETA, and DATA must all have the same number of elements.")
+        coef = np.empty((data.shape[0], self.nmodes))
+        tel = C.c_double(0.0)
+        check(self._L.zmf_fit(self._h, data.shape[0], _ptr(data), _ptr(coef), C.cast(C.byref(tel), C.c_void_p)))
+        return coef, tel.value
+
+
 _fitters = {}
+_sample_fitters = {}
+
+
+def _mode_table(N):
+    n = np.concatenate([[k] * (k + 1) for k in range(N + 1)]).astype(int)
+    m = np.concatenate([np.arange(-k, k + 1, 2) for k in range(N + 1)]).astype(int)
+    return np.column_stack([n, m])
+
+
+def _fit_samples(r, theta, data, N, device):
+    import hashlib
+    key = (hashlib.sha1(r.tobytes() + theta.tobytes()).hexdigest(), int(N), int(device))
+    f = _sample_fitters.get(key)
+    if f is None:
+        if len(_sample_fitters) >= 4:
+            _sample_fitters.pop(next(iter(_sample_fitters))).close()
+        f = _sample_fitters[key] = SampleFitter(r, theta, int(N), max_frames=64, device=device)
+    coef, _ = f.fit(data[None])
+    return np.column_stack([coef[0], np.zeros(f.nmodes)]), _mode_table(int(N))
 
 
 def zernmodfit(r, theta, data, N, device: int = 0):
@@ -121,7 +183,7 @@ def zernmodfit(r, theta, data, N, device: int = 0):
             if cnt > r.shape[0]:
                 break
     if key is None:
-        raise ValueError("zernmodfit (GPU): (r, theta) is not the driver's pupil grid (README.md:78-84)")
+        return _fit_samples(r, theta, data, N, device)          # any other sample set: zernmodfit.m:154-213 as it stands
     f = _fitters[key]
     nL = key[0]
     x = np.arange(-(nL - 1), nL, 2) / (nL - 1)
@@ -131,7 +193,7 @@ def zernmodfit(r, theta, data, N, device: int = 0):
     r_ref = np.hypot(X, Y).T.reshape(-1)[sel]
     th_ref = np.arctan2(Y, X).T.reshape(-1)[sel]
     if np.max(np.abs(r_ref - r)) > 1e-12 or np.max(np.abs(np.angle(np.exp(1j * (th_ref - theta))))) > 1e-12:
-        raise ValueError("zernmodfit (GPU): (r, theta) is not the driver's pupil grid (README.md:78-84)")
+        return _fit_samples(r, theta, data, N, device)          # as many samples as a pupil grid, but not that grid
     frame_cm = np.zeros(nL * nL)
     frame_cm[sel] = data
     frame = frame_cm.reshape(nL, nL).T

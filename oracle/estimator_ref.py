@@ -16,7 +16,8 @@ def estimate(A_s: np.ndarray, b_s: np.ndarray, y: np.ndarray) -> np.ndarray:
     out = np.empty((y.shape[0], A_s.shape[1]))
     for i in range(y.shape[0]):
         rhs = A_s.T @ (y[i] - b_s)
-        out[i] = np.linalg.lstsq(G, rhs, rcond=None)[0]
+        # minimum-norm least squares; lsqminnorm's default rank tolerance max(size(G)) * eps(norm(G)) = numpy's rcond = n * eps
+        out[i] = np.linalg.lstsq(G, rhs, rcond=G.shape[0] * np.finfo(float).eps)[0]
     return out
 
 

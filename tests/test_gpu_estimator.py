@@ -53,11 +53,23 @@ def test_estimator_other_shapes_and_errors(pk):
     y = rs.randn(2, 50)
     assert relerr(est.estimate(y)[0], er.estimate_pinv(A0, np.zeros(50), y)) < 1e-9
     est.close()
-    A = rs.randn(30, 4)
-    A[:, 3] = A[:, 0]                                                  # rank deficient
-    with pytest.raises(pk.FmpcError) as e:
-        pk.Estimator(A, None)
-    assert e.value.code == -13
+    # rank-deficient A_s: lsqminnorm's minimum-norm solution (README.md:478), tolerance 1e-10 like zernmodfit
+    for npix, nm, dup in ((30, 4, [(3, 0)]), (200, 27, [(5, 2), (20, 19)]), (64, 9, [(8, 0), (7, 0)])):
+        A = rs.randn(npix, nm)
+        for dst, src in dup:
+            A[:, dst] = A[:, src]                                      # duplicated columns
+        if nm == 27:
+            A[:, 11] = A[:, 3] - 2.0 * A[:, 4]                         # and a linear combination
+        b = rs.randn(npix)
+        y = rs.randn(5, npix)
+        est = pk.Estimator(A, b, max_batch=5)
+        xh, _ = est.estimate(y)
+        ref = er.estimate(A, b, y)                                     # Gram matrix + minimum-norm lstsq, one per measurement
+        assert relerr(xh, ref) < 1e-10
+        assert relerr(xh, er.estimate_pinv(A, b, y)) < 1e-9
+        for dst, src in dup:                                           # minimum norm: duplicated columns share the weight
+            assert np.abs(xh[:, dst] - xh[:, src]).max() < 1e-10 * np.abs(xh).max()
+        est.close()
     with pytest.raises(pk.FmpcError):
         pk.Estimator(rs.randn(3, 5), None)                             # more modes than pixels
 

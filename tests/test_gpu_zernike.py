@@ -68,6 +68,38 @@ def test_function_mirror(pk):
         pk.zernmodfit(r * 2, th, d, 4)
 
 
+@pytest.mark.parametrize("npts,N,nf", [(500, 4, 1), (3001, 6, 40), (12644, 6, 3), (257, 10, 9), (90, 11, 5)])
+def test_arbitrary_sample_sets(pk, npts, N, nf):
+    """zernmodfit.m:154-213 takes ANY sample vectors (its docstring example :21-90 uses a Cartesian patch of `peaks`):
+    random points in the unit disk, GPU fit (zmf_create_samples) against the oracle's zernmodfit per data vector."""
+    rs = np.random.RandomState(1000 + npts)
+    r = np.sqrt(rs.rand(npts))
+    th = rs.uniform(-np.pi, np.pi, npts)
+    r[0], r[1] = 0.0, 1.0                                  # both ends of the allowed range
+    data = rs.randn(nf, npts)
+    sf = pk.SampleFitter(r, th, N, max_frames=nf)
+    coef, _ = sf.fit(data)
+    sf.close()
+    for j in range(nf):
+        ad_ref, _ = zr.zernmodfit(r, th, data[j], N)
+        assert relerr(coef[j], ad_ref[:, 0]) < TOL, j
+    # the function mirror takes the same route for anything that is not the driver's pupil grid
+    ad, nm = pk.zernmodfit(r, th, data[0], N)
+    ad_ref, nm_ref = zr.zernmodfit(r, th, data[0], N)
+    assert relerr(ad, ad_ref) < TOL and np.array_equal(nm, nm_ref) and np.all(ad[:, 1] == 0)
+
+
+def test_arbitrary_sample_sets_errors(pk):
+    rs = np.random.RandomState(3)
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        pk.SampleFitter(np.array([0.1, 1.2, 0.3]), np.zeros(3), 0)
+    with pytest.raises(pk.FmpcError):                      # fewer samples than modes
+        pk.SampleFitter(rs.rand(5), rs.rand(5), 3)
+    with pytest.raises(pk.FmpcError) as e:                 # all samples on one ray: the azimuthal modes are not determined
+        pk.SampleFitter(rs.rand(200), np.zeros(200), 4)
+    assert e.value.code == -13
+
+
 @pytest.mark.parametrize("nL,N,nf", [(128, 6, 1), (128, 6, 9), (128, 10, 70), (64, 2, 130), (128, 6, 4500), (20, 11, 33), (50, 4, 17)])
 def test_dmma_path_shapes(pk, nL, N, nf):
     """Every tile-count / frame-tile / split-K configuration of the DMMA kernel (and, for nL % 4 != 0 or > 72 modes,
