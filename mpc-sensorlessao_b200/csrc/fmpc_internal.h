@@ -90,6 +90,8 @@ struct GenSys {
     const double *Yx;                       // ((T+1) n)^2 row-major: C_x inv(Phi_xx) C_x'
     const double *Q2, *Q2f, *Qi, *Qif;      // n x n row-major: 2Q, 2Qf and their inverses
     const double *dumin, *dumax;            // m
+    int dense_r;                            // 1: R is a dense SPD matrix (box rows only): Phi_uu of a stage is dense m x m
+    const double *R2;                       // m x m row-major: R + R' (= 2R for symmetric R), dense_r only
 };
 
 // status words (mirror include/fmpc.h)

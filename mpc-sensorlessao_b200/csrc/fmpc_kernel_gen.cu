@@ -34,8 +34,8 @@ __device__ __forceinline__ void dmma_gen(double &c0, double &c1, const double a,
 }
 
 struct GenWs {      // per-CTA scratch layout (doubles)
-    size_t z, zt, dz, rd, h, hd, pd, nu, dnu, rp, rpt, bv, yv, tdiag, toff, minv, Y, total;
-    __host__ __device__ static GenWs make(int n, int m, int T, int ramp)
+    size_t z, zt, dz, rd, h, hd, pd, nu, dnu, rp, rpt, bv, yv, tdiag, toff, minv, E, Y, total;
+    __host__ __device__ static GenWs make(int n, int m, int T, int ramp, int dense_r = 0)
     {
         GenWs L;
         const size_t N = (size_t)T * (n + m), NE = (size_t)(T + 1) * n, tm = (size_t)T * m;
@@ -43,7 +43,8 @@ struct GenWs {      // per-CTA scratch layout (doubles)
         L.z = o; o += N; L.zt = o; o += N; L.dz = o; o += N; L.rd = o; o += N; L.h = o; o += N; L.hd = o; o += N; L.pd = o; o += N;
         L.nu = o; o += NE; L.dnu = o; o += NE; L.rp = o; o += NE; L.rpt = o; o += NE; L.bv = o; o += NE; L.yv = o; o += NE;
         L.tdiag = o; o += tm; L.toff = o; o += tm;
-        L.minv = o; o += ramp ? tm * T : tm;
+        L.minv = o; o += dense_r ? tm * m : (ramp ? tm * T : tm);       // dense R: inv(Phi_uu) of every stage, m x m each
+        L.E = o; o += dense_r ? (size_t)(T + 1) * 4 * n * m : 0;          // dense R: C_u inv(Phi_uu) per (block row, u block)
         o = (o + 15) & ~(size_t)15;
         L.Y = o; o += NE * NE;
         L.total = (o + 15) & ~(size_t)15;
@@ -90,7 +91,15 @@ __device__ __forceinline__ double gen_rd_elem(const DevSys &S, const GenSys &G, 
 {
     const int n = G.n, m = G.m, st = n + m;
     const int t = c / st, j = c - t * st;
-    if (j < m) return __dadd_rn(__dadd_rn(__fma_rn(S.r2[j], z[c], S.rl[j]), hv), pd[c]);
+    if (j < m) {
+        if (G.dense_r) {                                       // 2 R u + r : dense row of R + R'
+            const double *R2 = G.R2 + (size_t)j * m, *u = z + (size_t)t * st;
+            double s = 0.0;
+            for (int jj = 0; jj < m; ++jj) s = fma(__ldg(R2 + jj), u[jj], s);
+            return __dadd_rn(__dadd_rn(__dadd_rn(s, S.rl[j]), hv), pd[c]);
+        }
+        return __dadd_rn(__dadd_rn(__fma_rn(S.r2[j], z[c], S.rl[j]), hv), pd[c]);
+    }
     const int k = j - m;
     const bool last = (t == G.T - 1);
     const double *Q2 = (last ? G.Q2f : G.Q2) + (size_t)k * n;
@@ -107,7 +116,11 @@ __device__ void gen_apply_phi_inv(const DevSys &S, const GenSys &G, const double
     for (int e = threadIdx.x; e < T * m; e += blockDim.x) {
         const int t = e / m, j = e - t * m;
         double s;
-        if (G.ramp) {
+        if (G.dense_r) {
+            const double *M = minv + ((size_t)t * m + j) * m, *vu = v + (size_t)t * st;
+            s = 0.0;
+            for (int jj = 0; jj < m; ++jj) s = fma(M[jj], vu[jj], s);
+        } else if (G.ramp) {
             s = 0.0;
             for (int tp = 0; tp < T; ++tp) s = fma(minv[((size_t)t * T + tp) * m + j], v[(size_t)tp * st + j], s);
         } else {
@@ -132,7 +145,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
     const int NB = T + (A.has_xf ? 1 : 0), NE = NB * n;
     const int ld = n | 1;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    const GenWs L = GenWs::make(n, m, T, G.ramp);
+    const GenWs L = GenWs::make(n, m, T, G.ramp, G.dense_r);
 
     double *bS = smem;                                  // n x ld : diagonal block
     double *sm_y = bS + (size_t)n * ld;                 // n
@@ -145,7 +158,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
     double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
     double *z = ws + L.z, *zt = ws + L.zt, *dz = ws + L.dz, *rd = ws + L.rd, *h = ws + L.h, *hd = ws + L.hd, *pd = ws + L.pd;
     double *nu = ws + L.nu, *dnu = ws + L.dnu, *rp = ws + L.rp, *rpt = ws + L.rpt, *bv = ws + L.bv, *yv = ws + L.yv;
-    double *tdiag = ws + L.tdiag, *toff = ws + L.toff, *minv = ws + L.minv, *Y = ws + L.Y;
+    double *tdiag = ws + L.tdiag, *toff = ws + L.toff, *minv = ws + L.minv, *Y = ws + L.Y, *Eb = ws + L.E;
     const size_t ldy = (size_t)NE;
 
     for (;;) {
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
                     }
                 }
                 pd[c] = A.kappa * g;
-                tdiag[e] = S.r2[j] + A.kappa * dd;
+                tdiag[e] = (G.dense_r ? 0.0 : S.r2[j]) + A.kappa * dd;      // dense R: the barrier part only, R + R' is added below
                 toff[e] = off;
             }
             for (int e = tid; e < T * n; e += nt) { const int t = e / n; pd[(size_t)t * st + m + (e - t * n)] = 0.0; }
@@ -239,7 +252,76 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             // ---- inv(Phi_uu): per-actuator tridiagonal LDL' (in place: tdiag <- d, toff <- l) and explicit inverse ----
             if (tid == 0) s_flag = 0;
             __syncthreads();
-            if (G.ramp) {
+            if (G.dense_r) {
+                // dense R (fast_mpc_objective.m:20-21 takes any square R): Phi_uu of stage t = (R + R') + k diag(d.^2) is a dense
+                // SPD m x m matrix.  Packed lower Cholesky in shared memory (the panel area is free here), explicit inverse of
+                // the factor column by column, inv(Phi_uu) = inv(L)' inv(L) to the scratch; then E = C_u inv(Phi_uu) per
+                // (block row, u block) for the Schur assembly.
+                double *Lp = panel, *Xp = panel + (size_t)m * (m + 1) / 2;
+                auto ix = [](int r, int c) { return (size_t)r * (r + 1) / 2 + c; };
+                for (int t = 0; t < T; ++t) {
+                    __syncthreads();
+                    for (int e = tid; e < m * m; e += nt) {
+                        const int r = e / m, c = e - r * m;
+                        if (c <= r) Lp[ix(r, c)] = __ldg(G.R2 + e) + (r == c ? tdiag[(size_t)t * m + r] : 0.0);
+                    }
+                    __syncthreads();
+                    for (int k = 0; k < m; ++k) {
+                        const double akk = Lp[ix(k, k)];
+                        __syncthreads();
+                        if (!(akk > 0.0)) { if (tid == 0) s_flag = 1; break; }
+                        const double dk = sqrt(akk);
+                        if (tid == 0) Lp[ix(k, k)] = dk;
+                        for (int r = k + 1 + tid; r < m; r += nt) Lp[ix(r, k)] /= dk;
+                        __syncthreads();
+                        const int rem = m - 1 - k;                      // trailing lower triangle of size rem
+                        for (int e = tid; e < rem * (rem + 1) / 2; e += nt) {
+                            int rr = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+                            while ((rr + 1) * (rr + 2) / 2 <= e) ++rr;
+                            while (rr * (rr + 1) / 2 > e) --rr;
+                            const int cc = e - rr * (rr + 1) / 2;
+                            const int r = k + 1 + rr, c = k + 1 + cc;
+                            Lp[ix(r, c)] = fma(-Lp[ix(r, k)], Lp[ix(c, k)], Lp[ix(r, c)]);
+                        }
+                        __syncthreads();
+                    }
+                    __syncthreads();
+                    if (s_flag) break;
+                    for (int c = tid; c < m; c += nt) {                 // column c of inv(L)
+                        Xp[ix(c, c)] = 1.0 / Lp[ix(c, c)];
+                        for (int r = c + 1; r < m; ++r) {
+                            double sacc = 0.0;
+                            for (int k = c; k < r; ++k) sacc = fma(Lp[ix(r, k)], Xp[ix(k, c)], sacc);
+                            Xp[ix(r, c)] = -sacc / Lp[ix(r, r)];
+                        }
+                    }
+                    __syncthreads();
+                    double *Mt = minv + (size_t)t * m * m;
+                    for (int e = tid; e < m * m; e += nt) {
+                        const int r = e / m, c = e - r * m;
+                        if (c > r) continue;
+                        double sacc = 0.0;
+                        for (int k = r; k < m; ++k) sacc = fma(Xp[ix(k, r)], Xp[ix(k, c)], sacc);
+                        Mt[(size_t)r * m + c] = sacc;
+                        Mt[(size_t)c * m + r] = sacc;
+                    }
+                }
+                __syncthreads();
+                if (!s_flag) {
+                    for (int i = 0; i < NB; ++i)
+                        for (int a = 0; a < G.ue_cnt[i]; ++a) {
+                            const double *Ca = G.cu + G.ue_ptr[4 * i + a];
+                            const double *Mt = minv + (size_t)G.ue_t[4 * i + a] * m * m;
+                            double *Ea = Eb + ((size_t)i * 4 + a) * n * m;
+                            for (int e = tid; e < n * m; e += nt) {
+                                const int r = e / m, j = e - r * m;
+                                double sacc = 0.0;
+                                for (int jj = 0; jj < m; ++jj) sacc = fma(__ldg(Ca + (size_t)r * m + jj), Mt[(size_t)jj * m + j], sacc);
+                                Ea[e] = sacc;
+                            }
+                        }
+                }
+            } else if (G.ramp) {
                 for (int j = tid; j < m; j += nt) {
                     double d = tdiag[j];
                     bool bad = !(d > 0.0);
@@ -293,23 +375,25 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
                     double c0 = 0.0, c1 = 0.0;
                     for (int a = 0; a < G.ue_cnt[i]; ++a) {
                         const int ta = G.ue_t[4 * i + a];
-                        const double *Ca = G.cu + G.ue_ptr[4 * i + a] + (size_t)min(ra, n - 1) * m;
+                        const double *Ca = G.dense_r ? Eb + ((size_t)i * 4 + a) * n * m + (size_t)min(ra, n - 1) * m
+                                                     : G.cu + G.ue_ptr[4 * i + a] + (size_t)min(ra, n - 1) * m;
                         for (int bb = 0; bb < G.ue_cnt[k]; ++bb) {
                             const int tb = G.ue_t[4 * k + bb];
                             if (!G.ramp && ta != tb) continue;
-                            const double *cv = G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m;
+                            // dense R: the A operand is a row of E = C_a inv(Phi_uu) already; `ones` keeps one code path
+                            const double *cv = G.dense_r ? nullptr : (G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m);
                             const double *Cb = G.cu + G.ue_ptr[4 * k + bb] + (size_t)min(cb, n - 1) * m;
                             double e0 = 0.0, e1 = 0.0;
                             int jb = 0;                                       // warp-uniform loop bounds (mma.sync needs all lanes)
                             for (; jb + 8 <= m; jb += 8) {                    // two accumulation chains
                                 const int j = jb + q;
-                                dmma_gen(c0, c1, __ldg(Ca + j) * cv[j], __ldg(Cb + j));
-                                dmma_gen(e0, e1, __ldg(Ca + j + 4) * cv[j + 4], __ldg(Cb + j + 4));
+                                dmma_gen(c0, c1, cv ? __ldg(Ca + j) * cv[j] : Ca[j], __ldg(Cb + j));
+                                dmma_gen(e0, e1, cv ? __ldg(Ca + j + 4) * cv[j + 4] : Ca[j + 4], __ldg(Cb + j + 4));
                             }
                             for (; jb < m; jb += 4) {                         // remaining k-steps, columns >= m contribute zeros
                                 const int j = jb + q;
                                 const bool ok = j < m;
-                                dmma_gen(c0, c1, ok ? __ldg(Ca + j) * cv[j] : 0.0, ok ? __ldg(Cb + j) : 0.0);
+                                dmma_gen(c0, c1, ok ? (cv ? __ldg(Ca + j) * cv[j] : Ca[j]) : 0.0, ok ? __ldg(Cb + j) : 0.0);
                             }
                             c0 += e0; c1 += e1;
                         }
@@ -677,8 +761,23 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
         }
     }
 
+    // ---- dense R (box rows only): R + R' row-major; SPD checked once here (the per-stage factorisation re-checks) ----
+    bool rdiag = true;
+    std::vector<double> R2((size_t)m * m);
+    for (int r = 0; r < m; ++r)
+        for (int c = 0; c < m; ++c) {
+            R2[(size_t)r * m + c] = s->R[(size_t)c * m + r] + s->R[(size_t)r * m + c];
+            if (r != c && R2[(size_t)r * m + c] != 0.0) rdiag = false;
+        }
+    if (!rdiag) {
+        if (s->ramp_rows) return FMPC_ERR_UNSUPPORTED;           // dense R + ramp rows: Phi_uu is block tridiagonal in m x m blocks
+        std::vector<double> Rinv;
+        if (!spd_inverse(R2, m, Rinv)) return FMPC_ERR_NOT_PD;
+    }
+
     GenSys G{};
     G.n = n; G.m = m; G.T = T; G.N = N; G.ramp = s->ramp_rows ? 1 : 0; G.ldyx = NE;
+    G.dense_r = rdiag ? 0 : 1;
     bool ok = true;
 #define GUP(field, vec) do { G.field = gen_upload(allocs, vec); if (!G.field) ok = false; } while (0)
     GUP(cw, cw); GUP(cw_ptr, cw_ptr); GUP(cw_off, cw_off); GUP(cw_len, cw_len);
@@ -687,6 +786,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     std::vector<double> dumin(m, 0.0), dumax(m, 0.0);
     if (s->ramp_rows) { dumin.assign(s->du_min, s->du_min + m); dumax.assign(s->du_max, s->du_max + m); }
     GUP(dumin, dumin); GUP(dumax, dumax);
+    if (G.dense_r) GUP(R2, R2);
 #undef GUP
     if (!ok) return FMPC_ERR_CUDA;
 
@@ -700,7 +800,12 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     if (prow > NE - n) prow = NE - n;
     if (prow < 8) prow = 8;
     G.panel_rows = prow;
-    const size_t smem = fixed + (size_t)prow * ld * 8;
+    size_t smem = fixed + (size_t)prow * ld * 8;
+    if (G.dense_r) {        // the panel area doubles as the packed Cholesky factor of Phi_uu and its inverse (2 x m(m+1)/2 doubles)
+        const size_t need = fixed + (size_t)m * (m + 1) * 8;
+        if (need > budget) return FMPC_ERR_UNSUPPORTED;
+        if (need > smem) smem = need;
+    }
     if (cudaFuncSetAttribute(fmpc_solve_kernel_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FMPC_ERR_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_gen, GEN_THREADS, smem) != cudaSuccess || per_sm < 1)
@@ -710,7 +815,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     cfg->smem = smem;
     cfg->use_mma = 3;
     cfg->slots = cfg->grid;
-    cfg->ws_stride = GenWs::make(n, m, T, G.ramp).total;
+    cfg->ws_stride = GenWs::make(n, m, T, G.ramp, G.dense_r).total;
     *out = G;
     return FMPC_OK;
 }

@@ -102,7 +102,7 @@ def test_create_argument_errors_come_before_cuda(pk):
     assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(u_min=null)), 1, 0) == -7    # U_BOUND_SIZE
     assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(n=0)), 1, 0) == -2           # DIM
     dense = np.asfortranarray(np.eye(m) + 0.1)
-    assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(R=P(dense))), 1, 0) == -14   # UNSUPPORTED (dense R)
+    assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(R=P(dense))), 1, 0) == -16   # dense R is covered: fails only for lack of a GPU
     denseq = np.asfortranarray(np.eye(n) + 0.1)
     assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(Q=P(denseq))), 1, 0) == -16  # dense Q is covered: fails only for lack of a GPU
     assert L.fmpc_create(ctypes.byref(h), ctypes.byref(sys_(ramp_rows=1)), 1, 0) == -7   # ramp rows without du bounds

@@ -156,10 +156,59 @@ def test_gen_argument_errors(pk):
     assert e.value.code == -7
     hb.close()
     Rd = c["R"].copy(); Rd[0, 1] = Rd[1, 0] = 0.1
-    with pytest.raises(pk.FmpcError) as e:       # non-diagonal R is the one input no kernel covers
-        pk.FastMPCBatch(c["A1"], None, c["B"], c["Q"], Rd, c["Qf"], c["u_min"], c["u_max"], c["T"], c["x_min"], c["x_max"])
+    with pytest.raises(pk.FmpcError) as e:       # non-diagonal R together with ramp rows is the one combination not covered
+        pk.FastMPCBatch(c["A1"], None, c["B"], c["Q"], Rd, c["Qf"], c["u_min"], c["u_max"], c["T"], c["x_min"], c["x_max"],
+                        du_min=c["du_min"], du_max=c["du_max"], ramp_rows=True)
     assert e.value.code == -14
     c2 = var1_literal_case(314, 6, 9, 2, 1, 0.6, 0.15)
     with pytest.raises(pk.FmpcError) as e:       # literal C with T < 3: fast_mpc_eq_const.m:55 rewrites the row itself
         gen_handle(pk, c2, False, True)
+    assert e.value.code == -14
+
+
+def dense_spd(rs, m, scale=1.0):
+    G = rs.randn(m, m)
+    return scale * (np.eye(m) + 0.3 * G @ G.T / m)
+
+
+@pytest.mark.parametrize("cfg", [(401, 6, 5, 4, 3, 0.6, True, False, False), (402, 8, 12, 6, 2, 0.4, True, True, False),
+                                 (403, 7, 9, 5, 2, 0.5, False, False, True), (404, 12, 33, 7, 2, 0.5, True, False, True),
+                                 (405, 28, 144, 3, 1, 3.0, True, False, False)],
+                         ids=lambda g: f"s{g[0]}_n{g[1]}m{g[2]}T{g[3]}")
+def test_dense_R_matches_dense_oracle(pk, cfg):
+    """fast_mpc_objective.m:20-21 accepts any square R: a dense SPD R makes Phi_uu of every stage a dense m x m matrix
+    (general-structure kernel: packed Cholesky + explicit inverse per stage in shared memory).  VAR(2) and VAR(1), with and
+    without the terminal row, with dense Q as well, and at the README's input dimension m = 144."""
+    from oracle import fastmpc_dense as fd
+    from cases import dense_solve
+    seed, n, m, T, nb, umax, a2, xf, denseq = cfg
+    c = small_problem(seed, n, m, T, nb, umax, a2=a2, xf=xf, warm=True)
+    rs = np.random.RandomState(seed)
+    c["R"] = dense_spd(rs, m)
+    if denseq:
+        c["Q"] = dense_spd(rs, n, 3.0)
+        c["Qf"] = 2.0 * c["Q"]
+    niters = 4 if m < 100 else 2
+    hb = gen_handle(pk, c, False, False)
+    assert hb.kernel_kind == 3
+    out = hb.step(c["x0"], c["x0_pre"], c["w"], c["xf"], c["X0"], c["U0"], c["nu0"], kappa=0.01, niters=niters)
+    hb.close()
+    for b in range(nb):
+        z, st = dense_solve(fd, c, b, niters, 0.01)
+        U, X = fd.deinterleave(z, n, m, T)
+        assert relerr(out["U"][b], U.T) < TOL, f"U instance {b}"
+        assert relerr(out["X"][b], X.T) < TOL, f"X instance {b}"
+        assert out["iters"][b] == st["iters"]
+
+
+def test_dense_R_errors(pk):
+    c = small_problem(410, 5, 4, 3, 1, 0.5)
+    c["R"] = np.array([[1.0, 2.0, 0, 0], [2.0, 1.0, 0, 0], [0, 0, 1.0, 0], [0, 0, 0, 1.0]])       # symmetric, indefinite
+    with pytest.raises(pk.FmpcError) as e:
+        gen_handle(pk, c, False, False)
+    assert e.value.code == -13
+    c["R"] = dense_spd(np.random.RandomState(0), 4)
+    c["du_min"], c["du_max"] = -np.ones(4), np.ones(4)
+    with pytest.raises(pk.FmpcError) as e:                     # dense R together with ramp rows is not covered
+        gen_handle(pk, c, True, False)
     assert e.value.code == -14
