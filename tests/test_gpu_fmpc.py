@@ -203,9 +203,9 @@ def test_frontends_kappa_continuation(pk):
     nus = np.random.RandomState(7).rand(max(nouter, 5), 30)
     g, o = pk.Fast_MPC2(*args), fd.Fast_MPC2(*args)
     assert relerr(g.mpc_fixed_newton(3, nu0=nus[:nouter]), o.mpc_fixed_newton(3, nu0_list=list(nus[:nouter]))) < TOL
-    assert relerr(g.mpc_solve_full(nu0=nus[:nouter]), o.mpc_solve_full(nu0_list=list(nus[:nouter]))) < 1e-7
-    assert relerr(g.mpc_solve_check(0.01, 1.0, nu0=nus[:5]), o.mpc_solve_check(0.01, 1.0, nu0_list=list(nus[:5]))) < 1e-7
-    assert relerr(g.mpc_fixed_log(0.01, nu0=nus[0]), o.mpc_fixed_log(0.01, nu0=nus[0])) < 1e-7
+    assert relerr(g.mpc_solve_full(nu0=nus[:nouter]), o.mpc_solve_full(nu0_list=list(nus[:nouter]))) < TOL
+    assert relerr(g.mpc_solve_check(0.01, 1.0, nu0=nus[:5]), o.mpc_solve_check(0.01, 1.0, nu0_list=list(nus[:5]))) < TOL
+    assert relerr(g.mpc_fixed_log(0.01, nu0=nus[0]), o.mpc_fixed_log(0.01, nu0=nus[0])) < TOL
 
 
 def test_state_update(pk):
