@@ -90,10 +90,14 @@ __device__ __forceinline__ double warp_sum(double v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+// cp.async.cg: the scratch streams are read once and must not pass through L1 -- the 7 resident warps leave only ~29 KB of
+// the unified array to L1, which has to keep the pool of iterate-independent Schur blocks (Yd / Y1, __ldg) and the operand
+// rows the passes re-read.  Measured +10 % over .ca (profiles/r02_l1_bypass.log); bypassing L1 for the plain scratch loads as
+// well costs 1.5 %.
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
 {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // DRAM -> L2 prefetch of `bytes` bytes at p (one 128-byte line per lane and step); no registers are tied up
@@ -254,7 +258,7 @@ enum { K_RP = 0, K_NEWTON = 1, K_TRIAL = 2, K_NORM = 3 };
 constexpr int STREAM_RD = 4;
 __device__ __forceinline__ void cp_async16_s(const unsigned saddr, const double *gsrc)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
 }
 // per-lane piece table of one chunk shape (fixed over the chunks of a pass): 16-byte piece p = lane + 32 it covers
 // row p / PPR, columns 2 (p % PPR) .. +1 of the chunk
