@@ -581,6 +581,9 @@ def run_single_process(args):
     import torch
     import mpc_sensorlessao_b200 as pk
     from mpc_sensorlessao_b200 import synth
+    sys.stdout.flush()
+    real_stdout = os.dup(1)          # NCCL may print its version banner to stdout: keep stdout to the one JSON line
+    os.dup2(2, 1)
     name = args.config if args.config in CONFIGS else "c2"
     N, T, nbc, ub, scaling, _ = CONFIGS[name]
     G = args.gpus
@@ -629,6 +632,8 @@ def run_single_process(args):
                     "api": "fmpc_multi_step_r"},
             "newton_iters_per_solve": its / (nb * K), "aggregate_tflops": its * F / dt / 1e12, "gpu_launches": launches,
             "per_device_stats_last_step": st}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
