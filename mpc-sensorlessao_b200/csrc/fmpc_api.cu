@@ -567,9 +567,11 @@ long long fmpc_last_newton_iters(fmpc_handle *h)
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
     for (int p = 0; p < fmpc_handle::MAX_PART; ++p)
         if (cudaStreamSynchronize(h->s_k[p]) != cudaSuccess) return -1;
-    for (int p = 0; p < fmpc_handle::MAX_CHUNKS; ++p) {       // one counter block per (possibly concurrent) chunk launch
+    std::vector<char> blk(256 * fmpc_handle::MAX_CHUNKS);     // one counter block per (possibly concurrent) chunk launch: one copy
+    if (cudaMemcpy(blk.data(), h->counters.p, blk.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int p = 0; p < fmpc_handle::MAX_CHUNKS; ++p) {
         unsigned long long vp = 0;
-        if (cudaMemcpy(&vp, h->counters.as<char>() + 256 * p + 8, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        std::memcpy(&vp, blk.data() + 256 * p + 8, 8);
         v += vp;
     }
     return (long long)v;

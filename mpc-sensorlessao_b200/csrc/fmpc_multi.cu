@@ -169,14 +169,15 @@ int fmpc_multi_shard(const fmpc_multi *M, int nbatch, int g, int *first, int *co
 }
 fmpc_handle *fmpc_multi_handle(fmpc_multi *M, int g) { return (M && g >= 0 && g < M->G) ? M->h[g] : nullptr; }
 
-static void fill_stats(fmpc_multi *M, int g, int cb, const int *status, double te)
+static void fill_stats(fmpc_multi *M, int g, int cb, const int *status, double te, const int *iters = nullptr)
 {
     fmpc_multi_stats &s = M->last[g];
     std::memset(&s, 0, sizeof s);
     s.device = M->dev[g];
     s.n_solves = cb;
     s.device_seconds = te;
-    s.newton_iters = (double)fmpc_last_newton_iters(M->h[g]);
+    if (iters) { double t = 0.0; for (int b = 0; b < cb; ++b) t += iters[b]; s.newton_iters = t; }     // no device round trip
+    else s.newton_iters = (double)fmpc_last_newton_iters(M->h[g]);
     if (status) for (int b = 0; b < cb; ++b) { const int v = status[b]; if (v >= 0 && v < 5) s.status_hist[v < 3 ? v : 3] += 1.0; }
 }
 
@@ -200,7 +201,7 @@ int fmpc_multi_step(fmpc_multi *M, const fmpc_params *p, int nbatch, const doubl
             const int rc = fmpc_step(M->h[g], p, cb, at(x0, n), at(x0_pre, n), at(u_prev, m), at(w, T * n), at(xf, n), at(X0, T * n),
                                      at(U0, T * m), at(nu0, NBn), X + (size_t)b0 * T * n, U + (size_t)b0 * T * m,
                                      status ? status + b0 : nullptr, iters ? iters + b0 : nullptr, tep);
-            if (rc == FMPC_OK) fill_stats(M, g, cb, status ? status + b0 : nullptr, *tep);
+            if (rc == FMPC_OK) fill_stats(M, g, cb, status ? status + b0 : nullptr, *tep, iters ? iters + b0 : nullptr);
             return rc;
         });
     }
@@ -231,7 +232,7 @@ int fmpc_multi_step_r(fmpc_multi *M, const fmpc_params *p, int nbatch, int flags
                                        at(nu0, NBn), u0 + (size_t)b0 * m, X ? X + (size_t)b0 * T * n : nullptr,
                                        U ? U + (size_t)b0 * T * m : nullptr, status ? status + b0 : nullptr,
                                        iters ? iters + b0 : nullptr, tep);
-            if (rc == FMPC_OK) fill_stats(M, g, cb, status ? status + b0 : nullptr, *tep);
+            if (rc == FMPC_OK) fill_stats(M, g, cb, status ? status + b0 : nullptr, *tep, iters ? iters + b0 : nullptr);
             return rc;
         });
     }
