@@ -7,3 +7,9 @@ $S --tool memcheck python -m pytest tests/test_gpu_zernike.py tests/test_gpu_est
 $S --tool racecheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "s23_ or s21_" 2>&1 | tail -4
 $S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s310 or s305" 2>&1 | tail -4
 $S --tool racecheck python -m pytest tests/test_gpu_zernike.py tests/test_gpu_varid.py -m gpu -x -q -k "16-2 or 64-2-130 or 16-12-3 or 1-50" 2>&1 | tail -4
+# round 2: resident step (fused shifted warm start / U(:,0) extraction and the separate shift / extract kernels), the device MT19937
+# generator (memcheck + racecheck: one CTA, double-buffered blocks), the multi-device entry points, dense R, arbitrary sample sets
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc.py tests/test_gpu_multi.py -m gpu -x -q -k "resident or stream or multi" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "stream_on_device or resident_steps" 2>&1 | tail -4
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc_gen.py tests/test_gpu_zernike.py tests/test_gpu_estimator.py -m gpu -x -q -k "s401 or s403 or s404 or 500-4 or 257-10 or other_shapes" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s401 or s403" 2>&1 | tail -4
