@@ -152,7 +152,7 @@ struct WGeom {
         g.NTT = (T + 7) / 8;
         g.TP8 = 8 * g.NTT;
         g.NN = g.NPOT * g.NPOT;
-        g.WB = 2 * g.mpad;
+        g.WB = g.mpad;                                 // ONE staged w row: at C2 this keeps 7 warps within the 196 KB carve-out (L1 60 KB, not 28)
         if (g.WB < 128) g.WB = 128;                    // also holds the 4 x 32 vectors of the backward sweep
         //          B            A1, A2                umax umin r2 rl     q2 q2f ql qfl qi qif
         g.const_doubles = (size_t)n * g.LDB + 2 * ((size_t)n * g.LD) + 4 * (size_t)g.mpad + 6 * (size_t)g.npad;
@@ -884,13 +884,7 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
         if (i < T) {
             cp_async_wait<0>();
             __syncwarp();
-            const double *wb = c.wbuf() + (i & 1) * mpad + q;
-            if (i + 1 < T) {
-                double *wn = c.wbuf() + ((i + 1) & 1) * mpad;
-                const double *src = c.WV() + (size_t)(i + 1) * mpad;
-                for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(wn + 2 * ch, src + 2 * ch);
-            }
-            cp_async_commit();
+            const double *wb = c.wbuf() + q;
             // B diag(w_i) B'  (rows >= n of B read finite junk that only reaches unused rows / columns of S)
             const double *pB[CT];
 #pragma unroll
@@ -921,6 +915,13 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
 #pragma unroll
                 for (int rt = 0; rt < CT; ++rt) { fr[rt] = frn[rt]; af[rt] = afn[rt]; }
             }
+            // the single w buffer is free again: fetch the next row underneath the rest of this stage
+            __syncwarp();
+            if (i + 1 < T) {
+                const double *src = c.WV() + (size_t)(i + 1) * mpad;
+                for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf() + 2 * ch, src + 2 * ch);
+            }
+            cp_async_commit();
         }
         {   // + iterate-independent part of Y[i,i]; rhs row <- -beta_i
 #pragma unroll
