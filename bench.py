@@ -555,6 +555,48 @@ def measure_zmf(cx):
     return out
 
 
+def measure_c1_batch(cx, nb=4096):
+    """BASELINE.json configs[0] shape, batched: the reference's VAR_1 exactly as written (ramp-rate rows + its literal C),
+    n = 27, m = 144, T = 10, on the general-structure kernel; one batched solve of nb instances, warm-started."""
+    import torch
+    import mpc_sensorlessao_b200 as pk
+    from mpc_sensorlessao_b200 import synth
+    L, dev = cx.L, cx.dev
+    p = synth.make_problem(6, 10, var_order=1, drop_piston=True, u_bound=28.0)
+    wi = synth.warm_inputs(p, nb, seed=7)
+    rs = np.random.RandomState(8)
+    u_prev = wi["U0"][:, 0] + 0.01 * rs.randn(nb, p.m)
+    hb = pk.FastMPCBatch(p.A1, None, p.B, p.Q, p.R, p.Qf, p.u_min, p.u_max, p.T, p.x_min, p.x_max, du_min=p.du_min, du_max=p.du_max,
+                         ramp_rows=True, var1_literal_bug=True, max_batch=nb, device=cx.local_rank)
+    params = hb.params(KAPPA, NITERS, 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in dict(x0=wi["x0"], X0=wi["X0"], U0=wi["U0"], nu0=wi["nu0"],
+                                                                                u_prev=u_prev).items()}
+    X = torch.empty((nb, p.T, p.n), dtype=torch.float64, device=dev)
+    U = torch.empty((nb, p.T, p.m), dtype=torch.float64, device=dev)
+    st = torch.empty(nb, dtype=torch.int32, device=dev)
+    it = torch.empty(nb, dtype=torch.int32, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    stream = torch.cuda.Stream(dev)
+    ms = []
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = L.fmpc_step_d(hb._h, C.byref(params), nb, vp(d["x0"]), None, vp(d["u_prev"]), None, None, vp(d["X0"]), vp(d["U0"]),
+                           vp(d["nu0"]), vp(X), vp(U), vp(st), vp(it), C.c_void_p(stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if rc:
+            raise pk.FmpcError(rc, pk.strerror(rc))
+        ms.append(e0.elapsed_time(e1))
+    kind = hb.kernel_kind
+    hb.close()
+    t = float(np.median(ms[1:]))
+    return {"workload": f"VAR(1) fastMPC as the reference writes it (ramp rows + literal C), n={p.n}, m={p.m}, T={p.T}, {nb} instances, "
+                        f"niters={NITERS}, one batched solve (BASELINE.json configs[0] shape, batched)", "kernel_kind": kind,
+            "value": nb / t * 1e3, "unit": "solves/s", "kernel_ms": t, "newton_iters_per_solve": float(it.sum().item()) / nb,
+            "status_hist": np.bincount(st.cpu().numpy(), minlength=5).tolist()}
+
+
 def measure_closed_loop(cx, p, nb, K):
     """fmpc_closed_loop: K steps of nb loops in ONE call (aberration sequence up, logs down), MATLAB stream on the device."""
     import mpc_sensorlessao_b200 as pk
@@ -782,6 +824,7 @@ def main():
                                "value": 16384 * r5["K"] / (r5["total_ms"] * 1e-3), "unit": "solves/s",
                                "newton_iters_per_solve": r5["newton_iters"] / (16384 * r5["K"]), "roofline": roofline_of(cx, r5, p5, "sets")}
                 del r5
+                extra["c1_batch"] = measure_c1_batch(cx)
                 extra.update(measure_zmf(cx))
                 extra["closed_loop"] = measure_closed_loop(cx, p, 4096, 20)
             except Exception as e:          # a side workload must never cost the headline line

@@ -156,3 +156,29 @@ def test_library_mt19937_is_matlabs_default_stream(tmp_path):
     ref = np.random.RandomState(5489).random_sample(out.size)
     assert np.array_equal(out, ref)
     assert abs(out[0] - 0.8147236863931789) < 1e-16 and abs(out[1] - 0.9057919370756192) < 1e-16       # MATLAB: rand after start-up
+
+
+def test_batched_handle_checks_shapes_before_touching_the_gpu(pk):
+    """FastMPCBatch hands raw pointers to fmpc_create, which cannot see array sizes: the reference's dimension checks
+    (same error strings) run on the host first."""
+    import pytest
+    n, m, T = 4, 3, 5
+    A, B, Q, R = np.eye(n), np.ones((n, m)), np.eye(n), np.eye(m)
+    um = np.ones(m)
+    ok = dict(A1=A, A2=A, B=B, Q=Q, R=R, Qf=Q, u_min=-um, u_max=um, T=T)
+    def make(**kw):
+        a = dict(ok); a.update(kw)
+        return pk.FastMPCBatch(a["A1"], a["A2"], a["B"], a["Q"], a["R"], a["Qf"], a["u_min"], a["u_max"], a["T"],
+                               q=a.get("q"), r=a.get("r"), x_min=a.get("x_min"), x_max=a.get("x_max"))
+    with pytest.raises(ValueError, match="State stage cost"):
+        make(Q=np.eye(n + 1))
+    with pytest.raises(ValueError, match="Control stage cost"):
+        make(R=np.eye(m + 1))
+    with pytest.raises(ValueError, match="equality state dynamics"):
+        make(A2=np.eye(n + 1))
+    with pytest.raises(ValueError, match="cotrol iequality"):
+        make(u_max=np.ones(m - 1))
+    with pytest.raises(ValueError, match="Linear state cost"):
+        make(q=np.ones(n - 1))
+    with pytest.raises(ValueError, match="state inequality"):
+        make(x_min=-np.ones(n - 2), x_max=np.ones(n))
