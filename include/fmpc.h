@@ -46,7 +46,7 @@ enum {
     FMPC_ERR_B_SIZE         = -11,  /* fast_mpc_eq_const.m:31-32   'The equality control dynamics matrix size does not match' */
     FMPC_ERR_INIT_SIZE      = -12,  /* fast_mpc_init.m:13-14       'Initialization size mismatch (T*(n+m))' */
     FMPC_ERR_NOT_PD         = -13,  /* chol() failure on a problem-constant block (Q, Qf, R) */
-    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover (non-diagonal R with ramp rows, n > 72) */
+    FMPC_ERR_UNSUPPORTED    = -14,  /* valid reference input this build does not cover (non-diagonal R with ramp rows) */
     FMPC_ERR_BATCH          = -15,  /* nbatch > max_batch of the handle */
     FMPC_ERR_CUDA           = -16,  /* no usable sm_100 device / CUDA runtime error (no CPU fallback) */
     FMPC_ERR_PARAM          = -17   /* kappa <= 0, niters < 0, beta not in (0,1) ... */

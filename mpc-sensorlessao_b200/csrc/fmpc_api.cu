@@ -352,7 +352,7 @@ const char *fmpc_strerror(int code)
     case FMPC_ERR_B_SIZE: return "The equality control dynamics matrix size does not match";
     case FMPC_ERR_INIT_SIZE: return "Initialization size mismatch (T*(n+m))";
     case FMPC_ERR_NOT_PD: return "cost matrix is not positive definite";
-    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (non-diagonal R together with ramp rows, n > 72, or a literal VAR_1 C that MATLAB itself would reject; see DESIGN.md)";
+    case FMPC_ERR_UNSUPPORTED: return "input not covered by this build (non-diagonal R together with ramp rows, a state block too large for shared memory, or a literal VAR_1 C that MATLAB itself would reject; see DESIGN.md)";
     case FMPC_ERR_BATCH: return "nbatch exceeds the handle's max_batch";
     case FMPC_ERR_CUDA: return "no usable sm_100 CUDA device or CUDA runtime error (there is no CPU fallback)";
     case FMPC_ERR_PARAM: return "invalid solver parameter";
@@ -398,7 +398,9 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
     // general-structure kernel: VAR_1 ramp rows, the literal VAR_1 column placement, dense Q / Qf, dense R
     const bool lit = (s->var_order == 1) && s->var1_literal_bug;
     const bool dense_r = !is_diag(s->R, m);
-    const bool need_gen = s->ramp_rows || lit || dense_r || !is_diag(s->Q, n) || !is_diag(s->Qf, n);
+    // n > 72: the stage blocks of the block-banded kernels no longer fit shared memory; the general kernel (dense Schur complement,
+    // n x n diagonal block + row panel in shared memory) takes over -- the reference has no size limit (fast_mpc_eq_const.m:14)
+    const bool need_gen = s->ramp_rows || lit || dense_r || !is_diag(s->Q, n) || !is_diag(s->Qf, n) || n > 72;
     if (lit && T < 3) return FMPC_ERR_UNSUPPORTED;           // fast_mpc_eq_const.m:55 then rewrites the mis-placed row itself
     for (int k = 0; k < n; ++k)
         if (!(s->Q[(size_t)k * n + k] > 0.0) || !(s->Qf[(size_t)k * n + k] > 0.0)) return FMPC_ERR_NOT_PD;

@@ -85,15 +85,26 @@ def test_parity_vs_golden(pk, path):
 
 def test_kernel_selection(pk):
     """n <= 32 runs on the warp-per-instance DMMA kernel, 32 < n <= 72 on the CTA-per-instance DMMA kernel (never a
-    CPU path); larger blocks do not fit the shared-memory block chain and are refused."""
+    CPU path); larger blocks do not fit the shared-memory block chain and go to the general-structure kernel."""
     for n, kind in ((6, 2), (28, 2), (32, 2), (33, 1), (66, 1), (72, 1)):
         c = small_problem(1, n, 4, 3, 1, 1.0)
         hb = make_handle(pk, c)
         assert hb.kernel_kind == kind
         hb.close()
-    with pytest.raises(pk.FmpcError) as e:
-        make_handle(pk, small_problem(1, 73, 4, 3, 1, 1.0))
-    assert e.value.code == -14
+    hb = make_handle(pk, small_problem(1, 73, 4, 3, 1, 1.0))          # n > 72: the general-structure kernel takes over
+    assert hb.kernel_kind == 3
+    hb.close()
+
+
+def test_large_state_dimension_runs_on_the_general_kernel(pk, fref):
+    """The reference has no size limit (fast_mpc_eq_const.m:14); n > 72 does not fit the stage blocks of the block-banded
+    kernels and is solved by the general-structure kernel (dense Schur complement)."""
+    for kw in (dict(seed=71, n=80, m=10, T=4, nb=2, umax=0.5, warm=True), dict(seed=72, n=100, m=12, T=3, nb=2, umax=0.4, xf=True)):
+        c = small_problem(**kw)
+        out = gpu_solve(pk, c, 4, 0.01)
+        ref = ref_solve(fref, c, 4, 0.01)
+        assert_parity(out, ref, c["nb"])
+        assert np.array_equal(out["iters"], ref["iters"])
 
 
 def test_line_search_both_regimes(pk, fref):
