@@ -152,7 +152,7 @@ struct WGeom {
         g.NTT = (T + 7) / 8;
         g.TP8 = 8 * g.NTT;
         g.NN = g.NPOT * g.NPOT;
-        g.WB = g.mpad;                                 // ONE staged w row: at C2 this keeps 7 warps within the 196 KB carve-out (L1 60 KB, not 28)
+        g.WB = 2 * g.mpad + 128;                       // two staged w rows + the stash of the paired last tile row (forward_sweep)
         if (g.WB < 128) g.WB = 128;                    // also holds the 4 x 32 vectors of the backward sweep
         //          B            A1, A2                umax umin r2 rl     q2 q2f ql qfl qi qif
         g.const_doubles = (size_t)n * g.LDB + 2 * ((size_t)n * g.LD) + 4 * (size_t)g.mpad + 6 * (size_t)g.npad;
@@ -832,6 +832,48 @@ __device__ __forceinline__ void tile_T(double (&o)[2], const double (&t)[2], con
 }
 
 // ---------------------------------------------------------------------------------------------
+// B diag(w) B' into the lower tiles of s, software-pipelined operand loads.
+//   MODE 0 : every lower tile, one w row.
+//   MODE 1 : NPOT = 28 (n = 25..28): the last tile row has at most 4 real rows (24..27); its fragment rows 4..7 would multiply
+//            padding.  They take the rows 24..27 of the NEXT stage instead (A operand = B[24 + (gq & 3)] scaled by w_i for
+//            gq < 4 and by w_{i+1} for gq >= 4), so the last tile row of two consecutive stages costs one set of DMMAs.
+//            The column operand of tile (CT-1, CT-1) is B[24 + (gq & 3)] too: columns 28..31 only ever hold padding.
+//   MODE 2 : the stage whose last tile row was computed by its predecessor: tile rows 0 .. CT-2 only.
+// ---------------------------------------------------------------------------------------------
+template <int RT, int CT, int MODE>
+__device__ __forceinline__ void bwb_loop(double (&s)[RT][CT][2], const double *const (&pB)[CT], const double *pBl, const double *wb,
+                                         const double *wl, const int MK)
+{
+    constexpr int NR = (MODE == 2) ? CT - 1 : CT;          // tile rows computed
+    double fr[CT], af[CT];
+#pragma unroll
+    for (int rt = 0; rt < NR; ++rt) fr[rt] = (MODE == 1 && rt == CT - 1) ? pBl[0] : pB[rt][0];
+    {
+        const double wv = wb[0], wlv = (MODE == 1) ? wl[0] : 0.0;
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt) af[rt] = fr[rt] * ((MODE == 1 && rt == CT - 1) ? wlv : wv);
+    }
+#pragma unroll 4
+    for (int kk = 0; kk < MK; ++kk) {
+        // operands of the next step (the last step re-reads its own: harmless)
+        const int kn = (kk + 1 < MK) ? kk + 1 : kk;
+        const double wn = wb[4 * kn], wln = (MODE == 1) ? wl[4 * kn] : 0.0;
+        double frn[CT], afn[CT];
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt) frn[rt] = (MODE == 1 && rt == CT - 1) ? pBl[4 * kn] : pB[rt][4 * kn];
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt) afn[rt] = frn[rt] * ((MODE == 1 && rt == CT - 1) ? wln : wn);
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt) {
+#pragma unroll
+            for (int ct = 0; ct <= rt; ++ct) dmma(s[rt][ct], af[rt], fr[ct]);
+        }
+#pragma unroll
+        for (int rt = 0; rt < NR; ++rt) { fr[rt] = frn[rt]; af[rt] = afn[rt]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Band-2 block Cholesky of Y fused with the forward substitution (inf_newton_solver.m:27-31).
 // On return YV holds y = inv(L) (-beta).  Returns 0 or the failing stage + 1.
 // ---------------------------------------------------------------------------------------------
@@ -846,9 +888,12 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
     const bool cok0 = (8 * (CT - 1) + 2 * q) < NPOT, cok1 = (8 * (CT - 1) + 2 * q + 1) < NPOT;     // block columns < NPOT
     const bool nok0 = (8 * (CT - 1) + 2 * q) < n, nok1 = (8 * (CT - 1) + 2 * q + 1) < n;          // real columns < n
 
-    // stage the first w row
+    // stage the first two w rows: stage i reads slot i & 1 (a paired stage also the other one) and refills it with row i + 2
+    constexpr bool PAIR = (NPOT % 8 == 4) && (RT == CT);      // NPOT = 28: the last tile row is at most half full
     for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf() + 2 * ch, c.WV() + 2 * ch);
+    if (T > 1) for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf() + mpad + 2 * ch, c.WV() + mpad + 2 * ch);
     cp_async_commit();
+    double2 *stash = reinterpret_cast<double2 *>(c.wbuf() + 2 * mpad);     // [CT][16 lanes]: rows 24..27 of the next stage
 
     for (int i = 0; i < NB; ++i) {
         const bool has1 = (i + 1 < NB), has2 = (i + 2 < NB) && c.a2;
@@ -884,42 +929,37 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
         if (i < T) {
             cp_async_wait<0>();
             __syncwarp();
-            const double *wb = c.wbuf() + q;
+            const double *wb = c.wbuf() + (i & 1) * mpad + q;
             // B diag(w_i) B'  (rows >= n of B read finite junk that only reaches unused rows / columns of S)
             const double *pB[CT];
 #pragma unroll
             for (int rt = 0; rt < CT; ++rt) pB[rt] = c.sB() + (size_t)(8 * rt + gq) * c.LDB + q;
-            double fr[CT], af[CT];
+            const bool pair_now = PAIR && !(i & 1) && (i + 1 < T), pair_done = PAIR && (i & 1);
+            if (pair_now) {
+                const double *pBl = c.sB() + (size_t)(8 * (CT - 1) + (gq & 3)) * c.LDB + q;
+                const double *wl = c.wbuf() + (((gq < 4) ? i : i + 1) & 1) * mpad + q;
+                bwb_loop<RT, CT, 1>(sacc, pB, pBl, wb, wl, c.MK);
+                if (gq >= 4) {                                   // rows 24..27 of stage i + 1: kept for the next stage
 #pragma unroll
-            for (int rt = 0; rt < CT; ++rt) fr[rt] = pB[rt][0];
-            {
-                const double wv = wb[0];
-#pragma unroll
-                for (int rt = 0; rt < CT; ++rt) af[rt] = fr[rt] * wv;
-            }
-#pragma unroll 4
-            for (int kk = 0; kk < c.MK; ++kk) {
-                // operands of the next step (the last step re-reads its own: harmless)
-                const int kn = (kk + 1 < c.MK) ? kk + 1 : kk;
-                const double wn = wb[4 * kn];
-                double frn[CT], afn[CT];
-#pragma unroll
-                for (int rt = 0; rt < CT; ++rt) frn[rt] = pB[rt][4 * kn];
-#pragma unroll
-                for (int rt = 0; rt < CT; ++rt) afn[rt] = frn[rt] * wn;
-#pragma unroll
-                for (int rt = 0; rt < CT; ++rt) {
-#pragma unroll
-                    for (int ct = 0; ct <= rt; ++ct) dmma(sacc[rt][ct], af[rt], fr[ct]);
+                    for (int ct = 0; ct < CT; ++ct) stash[16 * ct + 4 * (gq - 4) + q] = make_double2(sacc[CT - 1][ct][0], sacc[CT - 1][ct][1]);
                 }
+            } else if (pair_done) {
+                bwb_loop<RT, CT, 2>(sacc, pB, nullptr, wb, nullptr, c.MK);
 #pragma unroll
-                for (int rt = 0; rt < CT; ++rt) { fr[rt] = frn[rt]; af[rt] = afn[rt]; }
+                for (int ct = 0; ct < CT; ++ct) {
+                    const double2 v = stash[16 * ct + 4 * (gq & 3) + q];
+                    sacc[CT - 1][ct][0] = (gq < 4) ? v.x : 0.0;
+                    sacc[CT - 1][ct][1] = (gq < 4) ? v.y : 0.0;
+                }
+            } else {
+                bwb_loop<RT, CT, 0>(sacc, pB, nullptr, wb, nullptr, c.MK);
             }
-            // the single w buffer is free again: fetch the next row underneath the rest of this stage
+            // slot i & 1 is free again: fetch row i + 2 underneath the rest of this stage
             __syncwarp();
-            if (i + 1 < T) {
-                const double *src = c.WV() + (size_t)(i + 1) * mpad;
-                for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(c.wbuf() + 2 * ch, src + 2 * ch);
+            if (i + 2 < T) {
+                const double *src = c.WV() + (size_t)(i + 2) * mpad;
+                double *dst = c.wbuf() + (i & 1) * mpad;
+                for (int ch = lane; ch < mpad / 2; ch += 32) cp_async16(dst + 2 * ch, src + 2 * ch);
             }
             cp_async_commit();
         }
