@@ -72,17 +72,17 @@ __device__ __forceinline__ double rcp_nr(const double x)
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
-// 1/sqrt(x), x > 0 normal : MUFU.RSQ64H seed + two Newton steps
+// 1/sqrt(x), x > 0 normal : MUFU.RSQ64H seed + one cubic step
 __device__ __forceinline__ double rsqrt_nr(const double x)
 {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    // cubic (Halley) step: y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 : relative error 2^-20 -> ~2^-58; one cheap
-    // quadratic polish brings it to the last bit
-    double e = fma(-x * y, y, 1.0);
+    // cubic (Halley) step: y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 : the seed's relative error 2^-20 becomes ~2^-58, below the
+    // rounding of the result.  (Round 1 added a quadratic polish step on top: 4 more FP64 operations on the pivot chain of every
+    // column for nothing measurable -- all parity tests incl. iteration counts are unchanged without it, +1.3 % throughput.)
+    const double e = fma(-x * y, y, 1.0);
     y = fma(y * e, fma(0.375, e, 0.5), y);
-    e = fma(-x * y, y, 1.0);
-    return fma(0.5 * y, e, y);
+    return y;
 }
 __device__ __forceinline__ double warp_sum(double v)
 {
