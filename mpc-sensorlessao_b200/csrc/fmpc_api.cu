@@ -173,7 +173,8 @@ struct fmpc_handle {
     size_t ws_stride = 0;
     // MATLAB's default stream on the device (nu0 == NULL): MT19937 state (624 words + read index) and two buffers of stream
     // doubles.  nu_buf[nu_cur][0 .. nu_have) are the next unread doubles, generated on s_gen ahead of the call that uses them.
-    DevBuf d_mt, nu_buf[2];
+    DevBuf d_mt, d_mt_raw, nu_buf[2];
+    int mt_idx = 624;                     // next unread word of the block stored in d_mt (624: nothing unread)
     int nu_cur = 0;
     size_t nu_have = 0, nu_cap = 0;
     cudaStream_t s_gen = nullptr;
@@ -367,7 +368,7 @@ void fmpc_destroy(fmpc_handle *h)
     for (void *p : h->sys_allocs) cudaFree(p);
     DevBuf *bufs[] = {&h->ws, &h->counters, &h->d_x0, &h->d_x0pre, &h->d_uprev, &h->d_w, &h->d_xf, &h->d_X, &h->d_U,
                       &h->d_nu0, &h->d_status, &h->d_iters, &h->d_a, &h->d_Uacc, &h->d_Xacc, &h->d_itacc,
-                      &h->d_mt, &h->nu_buf[0], &h->nu_buf[1], &h->r_X, &h->r_U, &h->r_x0, &h->r_x0pre, &h->r_u0};
+                      &h->d_mt, &h->d_mt_raw, &h->nu_buf[0], &h->nu_buf[1], &h->r_X, &h->r_U, &h->r_x0, &h->r_x0pre, &h->r_u0};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; ++i) { if (h->ev_nu_ready[i]) cudaEventDestroy(h->ev_nu_ready[i]); if (h->ev_nu_free[i]) cudaEventDestroy(h->ev_nu_free[i]); }
     if (h->s_gen) cudaStreamDestroy(h->s_gen);
@@ -514,10 +515,8 @@ int fmpc_create(fmpc_handle **out, const fmpc_sys *s, int max_batch, int device)
             cudaEventCreateWithFlags(&h->ev_stg_out[i], cudaEventDisableTiming) != cudaSuccess) ok = false;
     if (ok) {   // rand's generator as a fresh MATLAB session has it: MT19937 seeded with 5489, nothing drawn yet
         MT19937 g(5489u);
-        uint32_t st[625];
-        std::memcpy(st, g.mt, sizeof(g.mt));
-        st[624] = 624u;
-        if (h->d_mt.ensure(sizeof(st)) || cudaMemcpy(h->d_mt.p, st, sizeof(st), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+        if (h->d_mt.ensure(sizeof(g.mt)) || cudaMemcpy(h->d_mt.p, g.mt, sizeof(g.mt), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+        h->mt_idx = 624;
     }
     if (!ok) { fmpc_destroy(h); return FMPC_ERR_CUDA; }
     *out = h;
@@ -530,10 +529,8 @@ int fmpc_seed_stream(fmpc_handle *h, unsigned seed)
     CU_OK(cudaSetDevice(h->device));
     CU_OK(cudaStreamSynchronize(h->s_gen));         // doubles generated ahead from the old state are dropped
     MT19937 g(seed);
-    uint32_t st[625];
-    std::memcpy(st, g.mt, sizeof(g.mt));
-    st[624] = 624u;
-    CU_OK(cudaMemcpy(h->d_mt.p, st, sizeof(st), cudaMemcpyHostToDevice));
+    CU_OK(cudaMemcpy(h->d_mt.p, g.mt, sizeof(g.mt), cudaMemcpyHostToDevice));
+    h->mt_idx = 624;
     h->nu_have = 0;
     return FMPC_OK;
 }
@@ -588,16 +585,16 @@ static int nu_take(fmpc_handle *h, size_t need, cudaStream_t consumer, const dou
     const size_t cap = (size_t)h->max_batch * (size_t)(h->T + 1) * (size_t)h->n;
     if (need > cap) return FMPC_ERR_BATCH;
     if (h->nu_cap < cap) {
-        if (h->nu_buf[0].ensure(cap * 8) || h->nu_buf[1].ensure(cap * 8)) return FMPC_ERR_CUDA;
+        if (h->nu_buf[0].ensure(cap * 8) || h->nu_buf[1].ensure(cap * 8) || h->d_mt_raw.ensure((2 * cap + 1248) * 4)) return FMPC_ERR_CUDA;
         h->nu_cap = cap;
     }
     const int cur = h->nu_cur, oth = cur ^ 1;
     double *B = h->nu_buf[cur].as<double>(), *O = h->nu_buf[oth].as<double>();
     if (h->nu_have < need) {
         if (h->nu_free_pending[cur]) { CU_OK(cudaStreamWaitEvent(h->s_gen, h->ev_nu_free[cur], 0)); h->nu_free_pending[cur] = false; }
-        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), B + h->nu_have, need - h->nu_have, h->s_gen);
+        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), h->d_mt_raw.as<unsigned>(), &h->mt_idx, B + h->nu_have, need - h->nu_have, h->s_gen);
         CU_OK(cudaGetLastError());
-        h->launches += 1;
+        h->launches += 2;
         h->nu_have = need;
     }
     CU_OK(cudaEventRecord(h->ev_nu_ready[cur], h->s_gen));
@@ -609,9 +606,9 @@ static int nu_take(fmpc_handle *h, size_t need, cudaStream_t consumer, const dou
     if (left) CU_OK(cudaMemcpyAsync(O, B + need, left * 8, cudaMemcpyDeviceToDevice, h->s_gen));
     size_t have = left;
     if (left < need) {
-        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), O + left, need - left, h->s_gen);
+        fmpc_launch_mt_fill(h->d_mt.as<unsigned>(), h->d_mt_raw.as<unsigned>(), &h->mt_idx, O + left, need - left, h->s_gen);
         CU_OK(cudaGetLastError());
-        h->launches += 1;
+        h->launches += 2;
         have = need;
     }
     h->nu_cur = oth;

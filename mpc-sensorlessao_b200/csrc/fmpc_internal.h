@@ -114,8 +114,9 @@ void fmpc_launch_extract_first(int m, int T, int nbatch, const double *U, double
 void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const double *U, const double *x0, const int *iters,
                           double *Uacc, double *Xacc, int *itacc, void *stream);
 
-// MATLAB default stream MT19937 on the device: appends `count` doubles of the stream at `out` (out == NULL: skips them)
-void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count, void *stream);
+// MATLAB default stream MT19937 on the device: appends `count` doubles of the stream at `out`; *idx = next unread word of the
+// stored block (host-side bookkeeping), `raw` = staging for the raw words (>= 2 count + 1248)
+void fmpc_launch_mt_fill(unsigned *state, unsigned *raw, int *idx, double *out, unsigned long long count, void *stream);
 
 // kernel_mma.cu : CTA-per-instance DMMA path (n <= 72)
 int  fmpc_mma_config(const DevSys &S, int device, SolveLaunchCfg *cfg);          // 0 ok, <0 not applicable

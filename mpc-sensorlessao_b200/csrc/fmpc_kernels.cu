@@ -425,17 +425,20 @@ __global__ void fmpc_log_step_kernel(int n, int m, int T, int nbatch, int K, int
 
 // =============================================================================================
 // MATLAB's default global stream on the device: `nu = rand(length(b),1)` (inf_newton_solver.m:2) is MT19937 seeded with
-// 5489, doubles by genrand_res53.  ONE CTA walks the stream (it is one dependency chain).  The recurrence
-//     x[k+624] = x[k+397] ^ f(x[k], x[k+1])
-// reaches back 227 words, which would cost three barrier-separated phases per 624-word block; substituting the recurrence
-// into itself expresses EVERY word of the next block by words of the current one,
+// 5489, doubles by genrand_res53.  The stream is ONE dependency chain,
+//     x[k+624] = x[k+397] ^ f(x[k], x[k+1]),
+// which reaches back only 227 words (three barrier-separated phases per 624-word block); substituting the recurrence into itself
+// expresses EVERY word of the next block by words of the current one,
 //     n[e] = o[e+397] ^ f(o[e],o[e+1])                                                        e <  227
 //     n[e] = o[e+170] ^ f(o[e-227],o[e-226]) ^ f(o[e],o[e+1])                           227 <= e <  454
 //     n[e] = o[e- 57] ^ f(o[e-454],o[e-453]) ^ f(o[e-227],o[e-226]) ^ f(o[e],o[e+1])    454 <= e <  623
 //     n[623] = n[396] ^ f(o[623], n[0])      (both expanded the same way)
-// so a block costs ONE barrier: all threads form the next block and temper / store the current one from the same reads.
-// state[0..623] = current block, state[624] = next unread word (always even: a double takes two words and 624 is even, so
-// pairs never straddle blocks).  out == NULL skips `count` doubles.
+// so a block costs ONE barrier.  Two kernels:
+//   fmpc_mt_twist_kernel   : ONE CTA, one word per thread (operand indices are loop invariants, no divergence except word 623),
+//                            walks the chain and writes the raw blocks to global memory: ~500 cycles per block, the floor of one
+//                            LDS -> ALU -> STS -> barrier round trip (scripts/ubench/mt.cu, profiles/r02_mt_generator.log);
+//   fmpc_mt_convert_kernel : tempering + genrand_res53 of the raw words, embarrassingly parallel.
+// state[0..623] = the last generated block; the index of the next unread word lives on the host (fmpc_api.cu).
 // =============================================================================================
 __device__ __forceinline__ unsigned mt_f(unsigned a, unsigned b)
 {
@@ -447,70 +450,47 @@ __device__ __forceinline__ unsigned mt_temper(unsigned y)
     y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
     return y;
 }
-__device__ __forceinline__ unsigned mt_next_word(const unsigned *o, const int e)
+// raw[0..624) <- the stored block, raw[624 (b + 1) ..) <- the b-th new block, b < nblocks; state <- the last block
+__global__ void __launch_bounds__(640, 1) fmpc_mt_twist_kernel(unsigned *__restrict__ state, unsigned *__restrict__ raw, int nblocks)
 {
-    if (e < 227) return o[e + 397] ^ mt_f(o[e], o[e + 1]);
-    if (e < 454) return o[e + 170] ^ mt_f(o[e - 227], o[e - 226]) ^ mt_f(o[e], o[e + 1]);
-    if (e < 623) return o[e - 57] ^ mt_f(o[e - 454], o[e - 453]) ^ mt_f(o[e - 227], o[e - 226]) ^ mt_f(o[e], o[e + 1]);
-    const unsigned n0 = o[397] ^ mt_f(o[0], o[1]);
-    const unsigned n396 = o[566] ^ mt_f(o[169], o[170]) ^ mt_f(o[396], o[397]);
-    return n396 ^ mt_f(o[623], n0);
-}
-// The first MT_TWIST threads form the next block, the others temper and store the current one; both only read the current
-// block, so ONE CTA barrier per block hands it over.
-template <int MT_THREADS, int MT_TWIST>
-__global__ void __launch_bounds__(MT_THREADS, 1) fmpc_mt_fill_kernel(unsigned *__restrict__ state, double *__restrict__ out,
-                                                                     unsigned long long count)
-{
-    constexpr int MT_OUT = MT_THREADS - MT_TWIST, NTW = (624 + MT_TWIST - 1) / MT_TWIST, NOUT = (312 + MT_OUT - 1) / MT_OUT;
     __shared__ __align__(16) unsigned mt[2][624];
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 624; i += MT_THREADS) mt[0][i] = state[i];
-    int idx = (int)state[624], cur = 0;
-    unsigned long long done = 0;
+    const int e = threadIdx.x;
+    const bool act = e < 624, last = (e == 623);
+    if (act) { const unsigned v = state[e]; mt[0][e] = v; raw[e] = v; }
+    // loop-invariant operand indices of word e: x ^ f(a0,a1) ^ (f(b0,b1) & mb) ^ (f(c0,c1) & mc)
+    int ix = 0, ia0 = 0, ia1 = 0, ib0 = 0, ib1 = 0, ic0 = 0, ic1 = 0;
+    unsigned mb = 0u, mc = 0u;
+    if (e < 227) { ix = e + 397; ia0 = e; ia1 = e + 1; }
+    else if (e < 454) { ix = e + 170; ia0 = e; ia1 = e + 1; ib0 = e - 227; ib1 = e - 226; mb = ~0u; }
+    else if (e < 623) { ix = e - 57; ia0 = e; ia1 = e + 1; ib0 = e - 227; ib1 = e - 226; mb = ~0u; ic0 = e - 454; ic1 = e - 453; mc = ~0u; }
     __syncthreads();
-    if (idx >= 624 && count > 0) {          // nothing unread in the stored block: form the first one
-        for (int e = tid; e < 624; e += MT_THREADS) mt[1][e] = mt_next_word(mt[0], e);
-        __syncthreads();
-        cur = 1; idx = 0;
-    }
-    while (done < count) {
-        // invariant: block `cur` holds unread words from idx on
-        const unsigned long long left = count - done;
-        const int avail = (624 - idx) >> 1;
-        const int take = (left < (unsigned long long)avail) ? (int)left : avail;
-        const bool more = left > (unsigned long long)avail;          // another block is needed after this one
+    int cur = 0;
+    for (int b = 0; b < nblocks; ++b) {
         const unsigned *o = mt[cur];
-        if (tid < MT_TWIST) {
-            if (more) {
-                unsigned *w = mt[cur ^ 1];
-                unsigned v[NTW];
-#pragma unroll
-                for (int j = 0; j < NTW; ++j) { const int e = tid + MT_TWIST * j; if (e < 624) v[j] = mt_next_word(o, e); }
-#pragma unroll
-                for (int j = 0; j < NTW; ++j) { const int e = tid + MT_TWIST * j; if (e < 624) w[e] = v[j]; }
-            }
-        } else if (out) {
-#pragma unroll
-            for (int j = 0; j < NOUT; ++j) {
-                const int t = tid - MT_TWIST + MT_OUT * j;
-                if (t < take) {
-                    const uint2 y = *reinterpret_cast<const uint2 *>(o + idx + 2 * t);      // idx is even: 8-byte aligned
-                    const unsigned a = mt_temper(y.x) >> 5, b = mt_temper(y.y) >> 6;
-                    // (a 2^26 + b) 2^-53 without integer -> double conversions: both pieces are exact in the mantissa of 2^52 + v
-                    const double da = __longlong_as_double(0x4330000000000000ll | (long long)a) - 4503599627370496.0;
-                    const double db = __longlong_as_double(0x4330000000000000ll | (long long)b) - 4503599627370496.0;
-                    out[done + t] = (da * 67108864.0 + db) * (1.0 / 9007199254740992.0);
-                }
-            }
+        unsigned v;
+        if (!last) {
+            v = o[ix] ^ mt_f(o[ia0], o[ia1]) ^ (mt_f(o[ib0], o[ib1]) & mb) ^ (mt_f(o[ic0], o[ic1]) & mc);
+        } else {
+            const unsigned n0 = o[397] ^ mt_f(o[0], o[1]);
+            const unsigned n396 = o[566] ^ mt_f(o[169], o[170]) ^ mt_f(o[396], o[397]);
+            v = n396 ^ mt_f(o[623], n0);
         }
+        if (act) { mt[cur ^ 1][e] = v; raw[(size_t)(b + 1) * 624 + e] = v; }
         __syncthreads();
-        idx += 2 * take;
-        done += take;
-        if (more) { cur ^= 1; idx = 0; }
+        cur ^= 1;
     }
-    for (int i = tid; i < 624; i += MT_THREADS) state[i] = mt[cur][i];
-    if (tid == 0) state[624] = (unsigned)idx;
+    if (act) state[e] = mt[cur][e];
+}
+// out[i] = genrand_res53(raw[2 i], raw[2 i + 1])
+__global__ void fmpc_mt_convert_kernel(const unsigned *__restrict__ raw, double *__restrict__ out, unsigned long long count)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned a = mt_temper(raw[2 * i]) >> 5, b = mt_temper(raw[2 * i + 1]) >> 6;
+        // (a 2^26 + b) 2^-53 without integer -> double conversions: both pieces are exact in the mantissa of 2^52 + v
+        const double da = __longlong_as_double(0x4330000000000000ll | (long long)a) - 4503599627370496.0;
+        const double db = __longlong_as_double(0x4330000000000000ll | (long long)b) - 4503599627370496.0;
+        out[i] = (da * 67108864.0 + db) * (1.0 / 9007199254740992.0);
+    }
 }
 
 // =============================================================================================
@@ -576,12 +556,19 @@ void fmpc_launch_log_step(int n, int m, int T, int nbatch, int K, int k, const d
     fmpc_log_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, T, nbatch, K, k, U, x0, iters, Uacc, Xacc, itacc);
 }
 
-void fmpc_launch_mt_fill(unsigned *state, double *out, unsigned long long count, void *stream)
+// Appends `count` doubles of the stream at `out`.  *idx = next unread word of the stored block (624 = none), updated.
+// `raw` holds at least 2 count + 1248 words.
+void fmpc_launch_mt_fill(unsigned *state, unsigned *raw, int *idx, double *out, unsigned long long count, void *stream)
 {
-    // 8 warps form the next block, 4 store the current one: the fastest split measured (scripts/ubench/mt.cu,
-    // profiles/r02_mt_generator.log); a block costs ~500-700 cycles whatever the split -- one LDS -> ALU -> STS -> barrier
-    // round trip per 624 words is the floor of a single dependency chain
-    fmpc_mt_fill_kernel<384, 256><<<1, 384, 0, (cudaStream_t)stream>>>(state, out, count);
+    if (count == 0) return;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long need = 2 * count, avail = (unsigned long long)(624 - *idx);
+    const int nblk = (need > avail) ? (int)((need - avail + 623) / 624) : 0;
+    fmpc_mt_twist_kernel<<<1, 640, 0, st>>>(state, raw, nblk);
+    unsigned long long cb = (count + 255) / 256;
+    if (cb > 148 * 4) cb = 148 * 4;                       // a small grid: it shares the GPU with a running solve
+    fmpc_mt_convert_kernel<<<(int)cb, 256, 0, st>>>(raw + *idx, out, count);
+    *idx = (int)((unsigned long long)*idx + need - 624ull * (unsigned long long)nblk);
 }
 
 void fmpc_launch_shift_inplace(int n, int m, int T, int nbatch, double *X, double *U, void *stream)

@@ -65,6 +65,57 @@ __global__ void __launch_bounds__(THREADS, 1) k(unsigned *state, double *out, in
     if (acc == 12345.678) out[0] = acc;
     for (int i = tid; i < 624; i += THREADS) state[i] = mt[cur][i];
 }
+
+// ---- variant B: one word per thread, branch-free (7 loads + 3 twists, masks decide what enters), raw block stored to global ----
+template <int STORE>
+__global__ void __launch_bounds__(640, 1) kb(unsigned *state, unsigned *raw, int nblocks, long long *cyc)
+{
+    __shared__ __align__(16) unsigned mt[2][624];
+    const int e = threadIdx.x;
+    for (int i = e; i < 624; i += 640) { mt[0][i] = state[i]; mt[1][i] = 0u; }
+    // loop-invariant operand indices of word e
+    int ia0, ia1, ib0, ib1, ic0, ic1, ix;
+    unsigned mb = 0u, mc = 0u;
+    const bool act = e < 624, last = (e == 623);
+    if (e < 227) { ix = e + 397; ia0 = e; ia1 = e + 1; ib0 = ib1 = ic0 = ic1 = 0; }
+    else if (e < 454) { ix = e + 170; ia0 = e; ia1 = e + 1; ib0 = e - 227; ib1 = e - 226; mb = ~0u; ic0 = ic1 = 0; }
+    else { ix = e - 57; ia0 = e; ia1 = min(e + 1, 623); ib0 = e - 227; ib1 = e - 226; mb = ~0u; ic0 = e - 454; ic1 = e - 453; mc = ~0u; }
+    if (!act) { ix = ia0 = ia1 = ib0 = ib1 = ic0 = ic1 = 0; }
+    __syncthreads();
+    int cur = 0;
+    const long long t0 = clock64();
+    for (int b = 0; b < nblocks; ++b) {
+        const unsigned *o = mt[cur];
+        unsigned *w = mt[cur ^ 1];
+        unsigned v;
+        if (!last) {
+            const unsigned x = o[ix], a0 = o[ia0], a1 = o[ia1], b0 = o[ib0], b1 = o[ib1], c0 = o[ic0], c1 = o[ic1];
+            v = x ^ mt_f(a0, a1) ^ (mt_f(b0, b1) & mb) ^ (mt_f(c0, c1) & mc);
+        } else {
+            const unsigned n0 = o[397] ^ mt_f(o[0], o[1]);
+            const unsigned n396 = o[566] ^ mt_f(o[169], o[170]) ^ mt_f(o[396], o[397]);
+            v = n396 ^ mt_f(o[623], n0);
+        }
+        if (act) { w[e] = v; if (STORE) raw[(size_t)b * 624 + e] = v; }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const long long t1 = clock64();
+    if (e == 0) cyc[0] = t1 - t0;
+    if (act) state[e] = mt[cur][e];
+}
+template <int STORE> void runb(const char *name, unsigned *st, unsigned *raw, long long *cyc, int nb)
+{
+    kb<STORE><<<1, 640>>>(st, raw, nb, cyc);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    kb<STORE><<<1, 640>>>(st, raw, nb, cyc);
+    cudaEventRecord(e1); cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s threads  640: %.3f ms, %.0f cycles / block (%s)\n", name, ms, (double)c / nb, cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int THREADS, int TWIST, int MODE> void run(const char *name, unsigned *st, double *out, long long *cyc, int nb)
 {
     k<THREADS, TWIST, MODE><<<1, THREADS>>>(st, out, nb, cyc);
@@ -93,5 +144,8 @@ int main()
     run<1024, 640, 1>("twist only", st, out, cyc, nb);
     run<256, 128, 7>("all", st, out, cyc, nb);
     run<128, 96, 7>("all", st, out, cyc, nb);
+    unsigned *raw; cudaMalloc(&raw, (size_t)nb * 624 * 4);
+    runb<0>("B: branch-free twist, one word/thread", st, raw, cyc, nb);
+    runb<1>("B: same + raw block to global", st, raw, cyc, nb);
     return 0;
 }

@@ -113,8 +113,8 @@ def test_side_entry_points_validate_before_cuda(pk):
 def test_library_mt19937_is_matlabs_default_stream(tmp_path):
     """nu0 = NULL => rand(length(b),1) (inf_newton_solver.m:2) from MATLAB's default stream MT19937(5489).
     The host seeds the state (struct MT19937 of csrc/fmpc_api.cu, compiled here); the stream itself is generated on the
-    device, every word of the next 624-word block expressed by words of the current one (mt_next_word in
-    csrc/fmpc_kernels.cu) -- restated here in numpy with the kernel's index ranges and compared with numpy's MT19937; the kernel itself is checked by the -m gpu tests."""
+    device, every word of the next 624-word block expressed by words of the current one
+    (fmpc_mt_twist_kernel in csrc/fmpc_kernels.cu) -- restated here in numpy with the kernel's index ranges and compared with numpy's MT19937; the kernel itself is checked by the -m gpu tests."""
     import subprocess
     src = open(os.path.join(ROOT, "mpc-sensorlessao_b200", "csrc", "fmpc_api.cu")).read()
     a = src.index("struct MT19937 {")
@@ -138,7 +138,7 @@ def test_library_mt19937_is_matlabs_default_stream(tmp_path):
 
     o, out = seed_state.copy(), []
     for _ in range(7):                                  # 7 blocks = 2184 doubles
-        w = np.zeros(624, dtype=np.uint32)              # mt_next_word: every word of the next block from the current one
+        w = np.zeros(624, dtype=np.uint32)              # every word of the next block from the current one
         e = np.arange(0, 227)
         w[e] = o[e + 397] ^ twist(o[e], o[e + 1])
         e = np.arange(227, 454)
