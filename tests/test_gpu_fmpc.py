@@ -61,6 +61,13 @@ SMALL = [
     dict(seed=22, n=40, m=50, T=9, nb=3, umax=0.4, a2=False, warm=True),
     dict(seed=23, n=65, m=30, T=3, nb=2, umax=0.5),
     dict(seed=25, n=66, m=144, T=30, nb=150, umax=1.0, warm=True),   # C5 shape, more instances than SMs
+    # NPOT = 28 (n = 25..28): the last tile row of B diag(w) B' is shared by two consecutive stages -- odd and even horizons,
+    # every n of the class, with and without the terminal row, VAR(1)
+    dict(seed=26, n=25, m=33, T=7, nb=3, umax=0.4, warm=True),
+    dict(seed=27, n=26, m=20, T=4, nb=3, umax=0.4, warm=True, xf=True),
+    dict(seed=28, n=28, m=12, T=1, nb=2, umax=0.5),
+    dict(seed=29, n=27, m=9, T=3, nb=9, umax=0.3, a2=False, warm=True, xf=True),
+    dict(seed=30, n=28, m=144, T=21, nb=8, umax=0.5, warm=True),
 ]
 
 
