@@ -92,6 +92,10 @@ struct GenSys {
     const double *dumin, *dumax;            // m
     int dense_r;                            // 1: R is a dense SPD matrix (box rows only): Phi_uu of a stage is dense m x m
     const double *R2;                       // m x m row-major: R + R' (= 2R for symmetric R), dense_r only
+    int qdiag;                              // 1: Q and Qf are diagonal (the x part of 2 H z and inv(Phi_xx) need no dot products)
+    const int *sch; int nsch;               // Schur assembly tasks (pair, tile row, tile-column group), most expensive first
+    int cw_main, ls_stage;                  // line search: offset (into cw) of the window most block rows share; 1: it and the trial point fit the panel area
+    int cu_main;                            // offset (into cu) of the u block most block rows share: staged in shared memory for the Schur assembly
 };
 
 // status words (mirror include/fmpc.h)

@@ -17,7 +17,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
+#include <algorithm>
+#include <utility>
 #include "../../include/fmpc.h"
 #include "fmpc_internal.h"
 #include "fmpc_device.cuh"
@@ -27,6 +30,17 @@ using namespace fmpc_dev;
 namespace {
 
 constexpr int GEN_THREADS = 256;
+#ifndef GEN_MIN_CTAS
+#define GEN_MIN_CTAS 2
+#endif
+#ifdef FMPC_PROF   /* phase cycles of thread 0 of every CTA (fmpc_last_profile): init, barrier + residuals, inv(Phi_uu), rhs, Schur assembly,
+                      potrf + forward solve, panel, trailing update, backward substitution, dz, line search, accept + copy-out */
+#define GPROF_DECL long long p_acc[12]; long long p_last = clock64(); for (int i_ = 0; i_ < 12; ++i_) p_acc[i_] = 0;
+#define GPROF_T(idx) do { const long long now_ = clock64(); p_acc[idx] += now_ - p_last; p_last = now_; } while (0)
+#else
+#define GPROF_DECL
+#define GPROF_T(idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ void dmma_gen(double &c0, double &c1, const double a, const double b)
 {
@@ -46,24 +60,264 @@ struct GenWs {      // per-CTA scratch layout (doubles)
         L.minv = o; o += dense_r ? tm * m : (ramp ? tm * T : tm);       // dense R: inv(Phi_uu) of every stage, m x m each
         L.E = o; o += dense_r ? (size_t)(T + 1) * 4 * n * m : 0;          // dense R: C_u inv(Phi_uu) per (block row, u block)
         o = (o + 15) & ~(size_t)15;
-        L.Y = o; o += NE * NE;
+        L.Y = o; o += (NE + 1) * NE;                                       // + 1 row: the right-hand side of Y dnu = -beta
         L.total = (o + 15) & ~(size_t)15;
         return L;
     }
 };
 
-// out = C v (- bv)   : one warp per scalar row, lanes stride over the row window (coalesced)
-__device__ void gen_apply_C(const GenSys &G, int NB, const double *v, const double *bv, double *out)
+// leading dimension of a shared-memory operand of 8 x 4 DMMA fragments: a multiple of 4 with ld % 8 == 4, so that the 16 lanes of a
+// half-warp (rows gq = 0..3 / 4..7, columns q = 0..3) hit 16 different 8-byte banks
+__host__ __device__ __forceinline__ int gen_ld(int n) { int l = (n + 3) & ~3; if ((l & 7) != 4) l += 4; return l; }
+
+// e / d for 0 <= e < 2^32 / d with the precomputed magic = ceil(2^32 / d) (the copy loops divide by a run-time leading dimension)
+__device__ __forceinline__ unsigned gen_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
+__device__ __forceinline__ int gen_div(int e, unsigned magic) { return (int)__umulhi((unsigned)e, magic); }
+
+// NACT accumulation chains sharing one A fragment: acc[u] += A(8 x K) B_u(8 x K)' over K columns, 4 per step.  Ca / Cb[u] point at
+// this lane's fragment row; the main loop is straight-line (no guards) so that the loads of the next steps are issued ahead of the
+// products; only a last partial step (K % 4) is guarded.  SCALE: the A fragment is scaled by cv (the diagonal of the middle factor).
+template <int NACT, bool SCALE>
+__device__ __forceinline__ void gen_chains(double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int q)
+{
+    const int kf = K & ~3;
+#ifndef GEN_UNR
+#define GEN_UNR 2
+#endif
+    constexpr int unr = GEN_UNR;
+#pragma unroll unr
+    for (int jb = 0; jb < kf; jb += 4) {
+        const int j = jb + q;
+        double av = Ca[j];
+        if (SCALE) av *= cv[j];
+#pragma unroll
+        for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+    }
+    if (kf < K) {
+        const int j = kf + q;
+        const bool ok = j < K;
+        double av = ok ? Ca[j] : 0.0;
+        if (SCALE) av *= ok ? cv[j] : 0.0;
+#pragma unroll
+        for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, ok ? Cb[u][j] : 0.0);
+    }
+}
+template <bool SCALE>
+__device__ __forceinline__ void gen_chains_n(int nact, double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int q)
+{
+    if (nact == 4) gen_chains<4, SCALE>(acc, Ca, cv, Cb, K, q);
+    else if (nact == 3) gen_chains<3, SCALE>(acc, Ca, cv, Cb, K, q);
+    else if (nact == 2) gen_chains<2, SCALE>(acc, Ca, cv, Cb, K, q);
+    else gen_chains<1, SCALE>(acc, Ca, cv, Cb, K, q);
+}
+
+// The SCALE chains with the diagonal cv (K <= 256 doubles, K % 4 == 0) read once, coalesced, into registers (lane l holds cv[32 b + l])
+// and handed to the k-steps by shuffles: the per-step cv load from the global scratch (L1 holds little next to the streaming Y)
+// was the top stall of the Schur assembly.
+template <int NACT>
+__device__ __forceinline__ void gen_chains_cv(double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int lane)
+{
+    const int q = lane & 3;
+    double cr[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) cr[b] = (32 * b + lane < K) ? cv[32 * b + lane] : 0.0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (32 * b + 32 <= K) {                             // a whole block of 8 k-steps: straight-line, the loads run ahead of the products
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int j = 32 * b + 4 * kk + q;
+                const double av = Ca[j] * __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
+#pragma unroll
+                for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+            }
+        } else if (32 * b < K) {
+            const int kend = (K - 32 * b) >> 2;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const bool on = kk < kend;                  // warp-uniform; off-steps multiply zeros (addresses stay inside the row)
+                const int j = 32 * b + (on ? 4 * kk : 0) + q;
+                const double c = __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
+                const double av = on ? Ca[j] * c : 0.0;
+                if (on) {
+#pragma unroll
+                    for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+                }
+            }
+        }
+    }
+}
+__device__ __forceinline__ void gen_chains_cv_n(int nact, double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int lane)
+{
+    if (nact == 4) gen_chains_cv<4>(acc, Ca, cv, Cb, K, lane);
+    else if (nact == 3) gen_chains_cv<3>(acc, Ca, cv, Cb, K, lane);
+    else if (nact == 2) gen_chains_cv<2>(acc, Ca, cv, Cb, K, lane);
+    else gen_chains_cv<1>(acc, Ca, cv, Cb, K, lane);
+}
+
+// In-place lower Cholesky of the n x n block Sm (leading dimension ld, lower triangle read), then in-place inverse of the factor:
+// on return the lower triangle holds inv(L) and the strict upper triangle zeros.  One warp, a lane per row; left-looking so that
+// column k costs one pass over the finished columns instead of a rank-1 update of the whole trailing block; the reciprocal
+// square root replaces the square root + division pair.  rdiag (n) and tmp (n) are shared scratch.  Returns 0 or failing column + 1.
+__device__ int gen_potrf_inv(double *Sm, int n, int ld, int lane, double *rdiag, double *tmp)
+{
+    for (int k = 0; k < n; ++k) {
+        const double *rk = Sm + (size_t)k * ld;
+        for (int r = k + lane; r < n; r += 32) {
+            double *rr = Sm + (size_t)r * ld;
+            double s0 = rr[k], s1 = 0.0;
+            int j = 0;
+            for (; j + 1 < k; j += 2) { s0 = fma(-rr[j], rk[j], s0); s1 = fma(-rr[j + 1], rk[j + 1], s1); }
+            if (j < k) s0 = fma(-rr[j], rk[j], s0);
+            rr[k] = s0 + s1;
+        }
+        __syncwarp();
+        const double d = Sm[(size_t)k * ld + k];
+        if (!(d > 0.0)) return k + 1;                           // uniform across the warp
+        const double rs = rsqrt(d);
+        __syncwarp();
+        for (int r = k + lane; r < n; r += 32) Sm[(size_t)r * ld + k] *= rs;
+        if (lane == 0) rdiag[k] = rs;
+        __syncwarp();
+    }
+    // inv(L), last column first: X[j+1:, j] = -X[j+1:, j+1:] L[j+1:, j] / L[j][j]  (the trailing block is inverted already)
+    for (int j = n - 1; j >= 0; --j) {
+        const double xjj = rdiag[j];
+        for (int r = j + 1 + lane; r < n; r += 32) {
+            const double *rr = Sm + (size_t)r * ld;
+            double s0 = 0.0, s1 = 0.0;
+            int k = j + 1;
+            for (; k + 1 <= r; k += 2) { s0 = fma(rr[k], Sm[(size_t)k * ld + j], s0); s1 = fma(rr[k + 1], Sm[(size_t)(k + 1) * ld + j], s1); }
+            if (k <= r) s0 = fma(rr[k], Sm[(size_t)k * ld + j], s0);
+            tmp[r] = -(s0 + s1) * xjj;
+        }
+        __syncwarp();
+        for (int r = j + lane; r < n; r += 32) Sm[(size_t)r * ld + j] = (r == j) ? xjj : tmp[r];
+        __syncwarp();
+    }
+    return 0;
+}
+
+// 1/x for a positive normal x: MUFU.RCP64H seed + two Newton steps, no slow path
+__device__ __forceinline__ double gen_rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Same result as gen_potrf_inv for blocks whose padded size NP (= the leading dimension, <= 32) fits one lane per row: the row lives
+// in registers, S = U D U' right-looking with the pivot chain through shuffles (per column: shfl -> rcp -> 2 FMAs; the rank-1
+// update reads the column from a 32-double shared vector), then V = inv(U) column j by lane j and inv(L) = diag(1/sqrt(d)) V.
+// The shared-memory version pays three shared-memory round trips and a reciprocal square root per column (24 k + 42 k cycles
+// for n = 27, scripts/ubench/potrf.cu).  In place: U, then inv(L), overwrite Sm.  colbuf: 64 doubles, rsv: 32 doubles.
+template <int NP>
+__device__ __forceinline__ int gen_potrf_inv_reg(double *Sm, int n, int nrows, int lane, double *colbuf, double *rsv)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int ld = NP;
+    const int r = lane;
+    double a[NP];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) a[c] = (r < n && c < r) ? Sm[r * ld + c] : 0.0;
+    double diag = (r < n) ? Sm[r * ld + r] : 1.0;
+    double dpiv = 1.0;
+    int info = 0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const double d = __shfl_sync(FULL, diag, k);        // pivot of column k (lane k's diagonal entry)
+        if (!(d > 0.0) || !(d < 1.0e300)) { if (!info) info = k + 1; }
+        if (lane == k) dpiv = d;
+        const double at = a[k];                             // unscaled column entry
+        if (k + 1 < NP) {
+            double *cb = colbuf + (k & 1) * 32;
+            cb[lane] = at;
+            const double dinv = gen_rcp_pos(d);
+            const double t = at * dinv;                     // U(r,k)
+            a[k] = t;
+            diag = fma(-t, at, diag);                       // own diagonal entry (only lanes > k use it)
+            __syncwarp();
+            if ((k + 1) & 1) a[k + 1] = fma(-t, cb[k + 1], a[k + 1]);
+#pragma unroll
+            for (int c2 = (k + 2) & ~1; c2 + 1 < NP; c2 += 2) {
+                const double2 p = *reinterpret_cast<const double2 *>(cb + c2);
+                a[c2] = fma(-t, p.x, a[c2]);
+                a[c2 + 1] = fma(-t, p.y, a[c2 + 1]);
+            }
+        }
+    }
+    if (info) return info;                                  // uniform: d is the same in every lane
+    rsv[lane] = rsqrt(dpiv);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c + 1 < NP; c += 2)
+        if (r < NP) *reinterpret_cast<double2 *>(Sm + r * ld + c) = make_double2(a[c], a[c + 1]);
+    __syncwarp();
+    // V = inv(U): column j by lane j;  v[i] = -(sum_{k<i} U(i,k) v[k]) for i > j, v[j] = 1, v[i<j] = 0
+    const int j = lane;
+    double v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+            const double2 p = *reinterpret_cast<const double2 *>(Sm + i * ld + k);
+            s0 = fma(p.x, v[k], s0);
+            s1 = fma(p.y, v[k + 1], s1);
+        }
+        if (i & 1) s0 = fma(Sm[i * ld + i - 1], v[i - 1], s0);
+        v[i] = (i < j) ? 0.0 : ((i == j) ? 1.0 : -(s0 + s1));
+    }
+    __syncwarp();
+    const bool live = (j < n);
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (j < NP && i < nrows) Sm[i * ld + j] = (live && i < n) ? v[i] * rsv[i] : 0.0;      // inv(L)(i,j) = v(i,j) / sqrt(d_i)
+    return 0;
+}
+
+// one warp: factor + invert the diagonal block in bS (register version when the padded size fits a lane per row)
+__device__ __noinline__ int gen_potrf_dispatch(double *bS, int n, int ld, int nrb, int lane, double *sm_part, double *sm_y, double *sm_vec)
+{
+    if (ld == 28) return gen_potrf_inv_reg<28>(bS, n, nrb, lane, sm_part, sm_part + 64);       // sm_part (>= 96 doubles): column buffer + 1/sqrt(d)
+    if (ld == 20) return gen_potrf_inv_reg<20>(bS, n, nrb, lane, sm_part, sm_part + 64);
+    if (ld == 12) return gen_potrf_inv_reg<12>(bS, n, nrb, lane, sm_part, sm_part + 64);
+    if (ld == 4) return gen_potrf_inv_reg<4>(bS, n, nrb, lane, sm_part, sm_part + 64);
+    return gen_potrf_inv(bS, n, ld, lane, sm_y, sm_vec);
+}
+
+// out = C v (- bv)   : one warp per group of 4 scalar rows of a block row (they share the window of v: 5 loads per 4 products and 4
+// independent sums in flight), lanes stride over the row window (coalesced); per row the same summation order as a row per warp
+// win_s: shared-memory copy of the window matrix at offset win_ptr of G.cw (or nullptr)
+__device__ void gen_apply_C(const GenSys &G, int NB, const double *v, const double *bv, double *out, const double *win_s = nullptr, int win_ptr = -1)
 {
     const int n = G.n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int row = wid; row < NB * n; row += nw) {
-        const int i = row / n, k = row - i * n, len = G.cw_len[i];
-        const double *c = G.cw + G.cw_ptr[i] + (size_t)k * len;
+    const int ngrp = (n + 3) >> 2;
+    for (int task = wid; task < NB * ngrp; task += nw) {
+        const int i = task / ngrp, k0 = 4 * (task - i * ngrp), len = G.cw_len[i];
+        const bool ws = win_s && G.cw_ptr[i] == win_ptr;
+        const double *c = ws ? win_s : G.cw + G.cw_ptr[i];
         const double *vv = v + G.cw_off[i];
-        double s = 0.0;
-        for (int j = lane; j < len; j += 32) s = fma(__ldg(c + j), vv[j], s);
-        s = warp_sum(s);
-        if (lane == 0) out[row] = bv ? s - bv[row] : s;
+        const double *c0 = c + (size_t)k0 * len, *c1 = c + (size_t)min(k0 + 1, n - 1) * len;
+        const double *c2 = c + (size_t)min(k0 + 2, n - 1) * len, *c3 = c + (size_t)min(k0 + 3, n - 1) * len;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+        for (int j = lane; j < len; j += 32) {
+            const double x = vv[j];
+            s0 = fma(c0[j], x, s0);
+            s1 = fma(c1[j], x, s1);
+            s2 = fma(c2[j], x, s2);
+            s3 = fma(c3[j], x, s3);
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane < 4 && k0 + lane < n) {
+            const int row = i * n + k0 + lane;
+            const double sv = lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : s3));
+            out[row] = bv ? sv - bv[row] : sv;
+        }
     }
 }
 
@@ -105,7 +359,8 @@ __device__ __forceinline__ double gen_rd_elem(const DevSys &S, const GenSys &G, 
     const double *Q2 = (last ? G.Q2f : G.Q2) + (size_t)k * n;
     const double *x = z + (size_t)t * st + m;
     double s = 0.0;
-    for (int kk = 0; kk < n; ++kk) s = fma(__ldg(Q2 + kk), x[kk], s);
+    if (G.qdiag) s = fma(__ldg(Q2 + k), x[k], s);               // the other products are exact zeros: same value as the full dot
+    else for (int kk = 0; kk < n; ++kk) s = fma(__ldg(Q2 + kk), x[kk], s);
     return __dadd_rn(__dadd_rn(s, (last ? S.qfl : S.ql)[k]), hv);
 }
 
@@ -133,27 +388,29 @@ __device__ void gen_apply_phi_inv(const DevSys &S, const GenSys &G, const double
         const double *Qi = ((t == T - 1) ? G.Qif : G.Qi) + (size_t)k * n;
         const double *vx = v + (size_t)t * st + m;
         double s = 0.0;
-        for (int kk = 0; kk < n; ++kk) s = fma(__ldg(Qi + kk), vx[kk], s);
+        if (G.qdiag) s = fma(__ldg(Qi + k), vx[k], s);
+        else for (int kk = 0; kk < n; ++kk) s = fma(__ldg(Qi + kk), vx[kk], s);
         p[(size_t)t * st + m + k] = sign * s;
     }
 }
 
-__global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSys S, const GenSys G, const StepArgs A)
+__global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) fmpc_solve_kernel_gen(const DevSys S, const GenSys G, const StepArgs A)
 {
     extern __shared__ double smem[];
     const int n = G.n, m = G.m, T = G.T, N = G.N, st = n + m;
     const int NB = T + (A.has_xf ? 1 : 0), NE = NB * n;
-    const int ld = n | 1;
+    const int ld = gen_ld(n), n8 = (n + 7) & ~7, nrb = max(n8, ld);     // nrb: rows of the diagonal block buffer
+    const unsigned mg_ld = gen_magic(ld), mg_n = gen_magic(n);
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const GenWs L = GenWs::make(n, m, T, G.ramp, G.dense_r);
 
-    double *bS = smem;                                  // n x ld : diagonal block
-    double *sm_y = bS + (size_t)n * ld;                 // n
+    double *bS = smem;                                  // nrb x ld : diagonal block (rows / columns beyond n are zero)
+    double *sm_y = bS + (size_t)nrb * ld;               // n
     double *sm_vec = sm_y + n;                          // n
     double *sm_part = sm_vec + n;                       // nt
     double *red = sm_part + nt;                         // 34
     double *panel = red + 34;                           // panel_rows x ld
-    __shared__ int s_inst, s_flag;
+    __shared__ int s_inst, s_flag, s_task;
 
     double *ws = A.ws + (size_t)blockIdx.x * A.ws_stride;
     double *z = ws + L.z, *zt = ws + L.zt, *dz = ws + L.dz, *rd = ws + L.rd, *h = ws + L.h, *hd = ws + L.hd, *pd = ws + L.pd;
@@ -167,6 +424,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
         __syncthreads();
         const int b = s_inst;
         if (b >= A.nbatch) break;
+        GPROF_DECL
 
         const double *x0 = A.x0 + (size_t)b * n;
         const double *x0p = A.x0_pre ? A.x0_pre + (size_t)b * n : nullptr;
@@ -207,6 +465,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
         __syncthreads();
 
         int status = ST_OK, iters = 0;
+        GPROF_T(0);
         for (int it = 0; it < A.niters; ++it) {
             // ---- barrier terms: s = h - P z, d = 1./s, Phi_uu = 2R + k P'diag(d.^2)P  (inf_newton_KKT_H.m:3-13) ----
             for (int e = tid; e < T * m; e += nt) {
@@ -249,6 +508,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             if (!isfinite(nr0)) { status = ST_NONFINITE; break; }
             if (nr0 <= A.tol_r && sqrt(ssp) <= A.tol_p) { status = ST_EARLY_EXIT; break; }
 
+            GPROF_T(1);
             // ---- inv(Phi_uu): per-actuator tridiagonal LDL' (in place: tdiag <- d, toff <- l) and explicit inverse ----
             if (tid == 0) s_flag = 0;
             __syncthreads();
@@ -322,6 +582,10 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
                         }
                 }
             } else if (G.ramp) {
+                // per actuator: T = L D L' (unit lower bidiagonal L), then the inverse from  M[T-1][T-1] = 1/d_{T-1},
+                // M[t][t] = 1/d_t + l_t^2 M[t+1][t+1]  (all terms positive),  M[a][b] = -l_a M[a+1][b] for a < b, mirrored.
+                // A thread per actuator for the two T-step recurrences, then a thread per (column, actuator) for the products:
+                // no thread reads back what it stored and nothing is divided in the second pass.
                 for (int j = tid; j < m; j += nt) {
                     double d = tdiag[j];
                     bool bad = !(d > 0.0);
@@ -334,17 +598,22 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
                         if (!(d > 0.0)) bad = true;
                     }
                     if (bad) s_flag = 1;
-                    for (int tc = 0; tc < T; ++tc) {          // column tc of the inverse: L D L' x = e_tc
-                        double y = 1.0;
-                        for (int t = 0; t < tc; ++t) minv[((size_t)t * T + tc) * m + j] = 0.0;
-                        minv[((size_t)tc * T + tc) * m + j] = 1.0;
-                        for (int t = tc + 1; t < T; ++t) { y = -toff[(size_t)(t - 1) * m + j] * y; minv[((size_t)t * T + tc) * m + j] = y; }
-                        double x = minv[((size_t)(T - 1) * T + tc) * m + j] / tdiag[(size_t)(T - 1) * m + j];
-                        minv[((size_t)(T - 1) * T + tc) * m + j] = x;
-                        for (int t = T - 2; t >= 0; --t) {
-                            x = minv[((size_t)t * T + tc) * m + j] / tdiag[(size_t)t * m + j] - toff[(size_t)t * m + j] * x;
-                            minv[((size_t)t * T + tc) * m + j] = x;
-                        }
+                    double mm = 1.0 / d;
+                    minv[((size_t)(T - 1) * T + (T - 1)) * m + j] = mm;
+                    for (int t = T - 2; t >= 0; --t) {
+                        const double l = toff[(size_t)t * m + j];
+                        mm = fma(l * l, mm, 1.0 / tdiag[(size_t)t * m + j]);
+                        minv[((size_t)t * T + t) * m + j] = mm;
+                    }
+                }
+                __syncthreads();
+                for (int e = tid; e < T * m; e += nt) {
+                    const int bcol = e / m, j = e - bcol * m;
+                    double x = minv[((size_t)bcol * T + bcol) * m + j];
+                    for (int a2 = bcol - 1; a2 >= 0; --a2) {
+                        x *= -toff[(size_t)a2 * m + j];
+                        minv[((size_t)a2 * T + bcol) * m + j] = x;
+                        minv[((size_t)bcol * T + a2) * m + j] = x;
                     }
                 }
             } else {
@@ -352,6 +621,7 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             }
             __syncthreads();
             if (s_flag) { status = ST_NOT_PD; break; }
+            GPROF_T(2);
 
             // ---- rhs of  Y dnu = -beta,  beta = -r_p + C inv(Phi) r_d  (:28-29) ----
             gen_apply_phi_inv(S, G, minv, rd, dz, 1.0);
@@ -359,185 +629,292 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             gen_apply_C(G, NB, dz, nullptr, yv);
             __syncthreads();
             for (int e = tid; e < NE; e += nt) yv[e] = rp[e] - yv[e];
+            GPROF_T(3);
 
             // ---- Y = Yx + C_u inv(Phi_uu) C_u'  (lower block triangle, full diagonal blocks) ----
-            // One warp task per (block pair, 8 x 8 tile): the tile of  sum_ab C_a diag(cv_ab) C_b'  is a chain of FP64 tensor-pipe
-            // products over the m actuators (A = C_a[r][j] cv[j] scaled on the fly, B = C_b[c][j], both L1-resident).
+            // One warp task per (block pair, tile row, group of 4 tile columns): the tiles of  sum_ab C_a diag(cv_ab) C_b'  are chains
+            // of FP64 tensor-pipe products over the m actuators; the scaled A fragment is shared by the 4 tile columns (4 independent
+            // accumulation chains).  The u block most block rows share (G.cu_main: -B) is staged in shared memory (the panel area is
+            // free here) with a bank-conflict-free leading dimension -- from global memory every fragment load touches 8 cache lines
+            // and the L1 tag stage, not the FP64 pipe, sets the pace.  When both operands are the same block the n x n block is
+            // symmetric (diag(cv) is): only tiles on or below its diagonal are computed and mirrored.
             {
-                const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5, gq = lane >> 2, q = lane & 3;
-                const int ntl = (n + 7) / 8, npair = NB * (NB + 1) / 2, ntask = npair * ntl * ntl;
-                for (int task = wid; task < ntask; task += nw) {
-                    const int pr = task / (ntl * ntl), tl = task - pr * ntl * ntl, rt = tl / ntl, ct = tl - rt * ntl;
+                const int gq = lane >> 2, q = lane & 3;
+                const int ntl = n8 >> 3, ngrp = (ntl + 3) >> 2;
+                const int ldm = gen_ld(m);
+                const bool staged = G.cu_main >= 0;                       // host side: fits the panel area, diagonal R
+                if (staged) {
+                    const double *src = G.cu + G.cu_main;
+                    for (int e = tid; e < n8 * ldm; e += nt) {
+                        const int r = e / ldm, j = e - r * ldm;
+                        panel[e] = (r < n && j < m) ? __ldg(src + (size_t)r * m + j) : 0.0;
+                    }
+                }
+                for (int e = tid; e < NE; e += nt) Y[(size_t)NE * ldy + e] = yv[e];       // the right-hand side: last row of the factorisation
+                if (tid == 0) s_task = 0;
+                __syncthreads();
+                // tasks are handed out dynamically, most expensive first (host-side order): block rows with several u blocks (the
+                // literal VAR_1 second row) cost up to 16 x a symmetric single-tile task
+                for (;;) {
+                    int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&s_task, 1);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (slot >= G.nsch) break;
+                    const int task = G.sch[slot];
+                    const int pr = task / (ntl * ngrp), tl = task - pr * ntl * ngrp, rt = tl / ngrp, ct0 = 4 * (tl - rt * ngrp);
                     int i = 0;
                     while ((i + 1) * (i + 2) / 2 <= pr) ++i;
                     const int k = pr - i * (i + 1) / 2;
-                    const int ra = 8 * rt + gq, cb = 8 * ct + gq;             // A-operand row / B-operand row of this lane
-                    double c0 = 0.0, c1 = 0.0;
-                    for (int a = 0; a < G.ue_cnt[i]; ++a) {
-                        const int ta = G.ue_t[4 * i + a];
-                        const double *Ca = G.dense_r ? Eb + ((size_t)i * 4 + a) * n * m + (size_t)min(ra, n - 1) * m
-                                                     : G.cu + G.ue_ptr[4 * i + a] + (size_t)min(ra, n - 1) * m;
-                        for (int bb = 0; bb < G.ue_cnt[k]; ++bb) {
-                            const int tb = G.ue_t[4 * k + bb];
-                            if (!G.ramp && ta != tb) continue;
-                            // dense R: the A operand is a row of E = C_a inv(Phi_uu) already; `ones` keeps one code path
-                            const double *cv = G.dense_r ? nullptr : (G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m);
-                            const double *Cb = G.cu + G.ue_ptr[4 * k + bb] + (size_t)min(cb, n - 1) * m;
-                            double e0 = 0.0, e1 = 0.0;
-                            int jb = 0;                                       // warp-uniform loop bounds (mma.sync needs all lanes)
-                            for (; jb + 8 <= m; jb += 8) {                    // two accumulation chains
-                                const int j = jb + q;
-                                dmma_gen(c0, c1, cv ? __ldg(Ca + j) * cv[j] : Ca[j], __ldg(Cb + j));
-                                dmma_gen(e0, e1, cv ? __ldg(Ca + j + 4) * cv[j + 4] : Ca[j + 4], __ldg(Cb + j + 4));
-                            }
-                            for (; jb < m; jb += 4) {                         // remaining k-steps, columns >= m contribute zeros
-                                const int j = jb + q;
-                                const bool ok = j < m;
-                                dmma_gen(c0, c1, ok ? (cv ? __ldg(Ca + j) * cv[j] : Ca[j]) : 0.0, ok ? __ldg(Cb + j) : 0.0);
-                            }
-                            c0 += e0; c1 += e1;
+                    if (i >= NB) continue;                                    // terminal block row of a problem solved without xf
+                    const int na = G.ue_cnt[i], nbk = G.ue_cnt[k];
+                    const bool sym = na == 1 && nbk == 1 && G.ue_ptr[4 * i] == G.ue_ptr[4 * k] && (G.ramp || G.ue_t[4 * i] == G.ue_t[4 * k]);
+                    int nact = min(4, ntl - ct0);
+                    if (sym) nact = min(nact, rt - ct0 + 1);
+                    if (nact <= 0) continue;                                  // the whole group lies above the diagonal of a symmetric block
+                    const int ra = 8 * rt + gq;
+                    // the products accumulate on top of the constant x part of the tile (read here, ahead of the chain); a mirrored
+                    // tile needs  Yx[c][r] - Yx[r][c]  on top of that
+                    double acc[4][2], dm[4][2];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ct = ct0 + u, c = 8 * ct + 2 * q;
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            const bool on = u < nact && ra < n && c + v < n;
+                            acc[u][v] = on ? __ldg(G.Yx + ((size_t)i * n + ra) * G.ldyx + (size_t)k * n + c + v) : 0.0;
+                            dm[u][v] = (on && sym && ct < rt) ? __ldg(G.Yx + ((size_t)i * n + c + v) * G.ldyx + (size_t)k * n + ra) - acc[u][v] : 0.0;
                         }
                     }
-                    const int r = 8 * rt + gq, c = 8 * ct + 2 * q;
-                    if (r < n) {
-                        const double *yx = G.Yx + ((size_t)i * n + r) * G.ldyx + (size_t)k * n;
-                        double *yo = Y + ((size_t)i * n + r) * ldy + (size_t)k * n;
-                        if (c < n) yo[c] = __ldg(yx + c) + c0;
-                        if (c + 1 < n) yo[c + 1] = __ldg(yx + c + 1) + c1;
+                    for (int a = 0; a < na; ++a) {
+                        const int ta = G.ue_t[4 * i + a], pa = G.ue_ptr[4 * i + a];
+                        const bool sa = staged && pa == G.cu_main;
+                        const double *Ca = G.dense_r ? Eb + ((size_t)i * 4 + a) * n * m + (size_t)min(ra, n - 1) * m
+                                         : sa ? panel + (size_t)ra * ldm : G.cu + pa + (size_t)min(ra, n - 1) * m;
+                        for (int bb = 0; bb < nbk; ++bb) {
+                            const int tb = G.ue_t[4 * k + bb], pb = G.ue_ptr[4 * k + bb];
+                            if (!G.ramp && ta != tb) continue;
+                            // dense R: the A operand is a row of E = C_a inv(Phi_uu) already
+                            const double *cv = G.dense_r ? nullptr : (G.ramp ? minv + ((size_t)ta * T + tb) * m : minv + (size_t)ta * m);
+                            const bool sb = staged && pb == G.cu_main;
+                            const double *Cb[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int cb = min(8 * (ct0 + u) + gq, n8 - 1);
+                                Cb[u] = sb ? panel + (size_t)cb * ldm : G.cu + pb + (size_t)min(cb, n - 1) * m;
+                            }
+                            const bool cvreg = cv && m <= 256 && (m & 3) == 0;
+                            if (sa && sb && cvreg) {
+                                // both operands are the staged block: pointers formed from the shared array directly, so that the
+                                // loads are shared-memory loads (a generic load is tracked like a global one and the products wait on it)
+                                const double *CaS = panel + (size_t)ra * ldm;
+                                const double *CbS[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) CbS[u] = panel + (size_t)min(8 * (ct0 + u) + gq, n8 - 1) * ldm;
+                                gen_chains_cv_n(nact, acc, CaS, cv, CbS, m, lane);
+                            } else if (cvreg) gen_chains_cv_n(nact, acc, Ca, cv, Cb, m, lane);
+                            else if (cv) gen_chains_n<true>(nact, acc, Ca, cv, Cb, m, q);
+                            else gen_chains_n<false>(nact, acc, Ca, cv, Cb, m, q);
+                        }
+                    }
+                    const int r = 8 * rt + gq;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u >= nact) continue;
+                        const int ct = ct0 + u, c = 8 * ct + 2 * q;
+                        if (r >= n) continue;
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            if (c + v >= n) continue;
+                            Y[((size_t)i * n + r) * ldy + (size_t)k * n + c + v] = acc[u][v];
+                            if (sym && ct < rt)                               // mirror inside the symmetric u part of the block
+                                Y[((size_t)i * n + c + v) * ldy + (size_t)k * n + r] = acc[u][v] + dm[u][v];
+                        }
                     }
                 }
             }
             __syncthreads();
+            GPROF_T(4);
 
-            // ---- dense blocked Cholesky of Y fused with the forward substitution (:30-31) ----
+            // ---- dense blocked Cholesky of Y with the right-hand side as one more row (:30-31) ----
+            // Per block column K: the diagonal block goes to shared memory, warp 0 factors it and inverts the factor in place while the
+            // other warps stage the panel (all rows below, right-hand-side row included); panel <- panel inv(L_KK)' and the trailing
+            // update  Y[r,c] -= sum_j P[r,j] P[c,j]  run on the FP64 tensor pipe from shared memory (8 x 8 tiles, conflict-free
+            // leading dimension).  inv(L_KK) replaces L_KK in Y: the backward substitution multiplies by it instead of solving with
+            // L_KK.  After the last block the right-hand-side row holds y = inv(L) rhs.
             bool fail = false;
             for (int K = 0; K < NB; ++K) {
-                const int r0 = (K + 1) * n, R = NE - r0;          // trailing rows
+                const int gq = lane >> 2, q = lane & 3, nw = nt >> 5, ntl = n8 >> 3, nks = (n + 3) >> 2;
+                const int r0 = (K + 1) * n, R = NE - r0, Rp = R + 1;      // trailing rows; + the right-hand-side row
                 double *Ykk = Y + ((size_t)K * n) * ldy + (size_t)K * n;
-                for (int e = tid; e < n * n; e += nt) { const int r = e / n, c = e - r * n; bS[r * ld + c] = Ykk[(size_t)r * ldy + c]; }
-                for (int k = tid; k < n; k += nt) sm_y[k] = yv[K * n + k];
-                __syncthreads();
-                if (wid == 0) {
-                    const int info = warp_potrf(bS, n, ld, lane);
+                double *Yp0 = Y + (size_t)r0 * ldy + (size_t)K * n;
+                const bool whole = (Rp <= G.panel_rows);
+                // K > 0: the diagonal block was updated, factored and inverted by warp 0 during the trailing update of the step before
+                // (look-ahead: the serial factorisation of the small block is off the critical path); all warps stage the panel
+                if (K == 0) {
+                    for (int e = tid; e < nrb * ld; e += nt) {
+                        const int r = gen_div(e, mg_ld), c = e - r * ld;
+                        const double v = Ykk[(size_t)min(r, n - 1) * ldy + min(c, n - 1)];
+                        bS[e] = (r < n && c <= r) ? v : 0.0;
+                    }
+                    if (tid == 0) s_flag = 0;
+                    __syncthreads();
+                }
+                if (K == 0 && wid == 0) {
+                    const int info = gen_potrf_dispatch(bS, n, ld, nrb, lane, sm_part, sm_y, sm_vec);
                     if (lane == 0) s_flag = info;
+                } else {
+                    const int rc = min(G.panel_rows, Rp);
+                    const int t0 = (K == 0) ? tid - 32 : tid, ts = (K == 0) ? nt - 32 : nt;
+#pragma unroll 4
+                    for (int e = t0; e < rc * ld; e += ts) {
+                        const int r = gen_div(e, mg_ld), c = e - r * ld;
+                        const double v = Yp0[(size_t)r * ldy + min(c, n - 1)];
+                        panel[e] = (c < n) ? v : 0.0;
+                    }
                 }
                 __syncthreads();
                 if (s_flag) { fail = true; break; }
-                // y_K = inv(L_KK) rhs_K by the last warp, while the others write the factor back
-                if (wid == (nt >> 5) - 1) {
-                    for (int j = 0; j < n; ++j) {
-                        __syncwarp();
-                        const double yj = sm_y[j] / bS[j * ld + j];
-                        __syncwarp();
-                        if (lane == 0) sm_y[j] = yj;
-                        for (int k = j + 1 + lane; k < n; k += 32) sm_y[k] = fma(-bS[k * ld + j], yj, sm_y[k]);
-                    }
-                } else {
-                    for (int e = tid; e < n * n; e += nt - 32) { const int r = e / n, c = e - r * n; Ykk[(size_t)r * ldy + c] = (c <= r) ? bS[r * ld + c] : 0.0; }
-                }
-                __syncthreads();
-                for (int k = tid; k < n; k += nt) yv[K * n + k] = sm_y[k];
-                // panel: rows r0.. of block column K  <-  row * inv(L_KK)'  ; chunks of panel_rows rows through shared memory
-                const bool whole = (R <= G.panel_rows);
-                for (int c0 = 0; c0 < R; c0 += G.panel_rows) {
-                    const int rc = min(G.panel_rows, R - c0);
-                    double *Yp = Y + ((size_t)(r0 + c0)) * ldy + (size_t)K * n;
-                    __syncthreads();
-                    for (int e = tid; e < rc * n; e += nt) { const int r = e / n, c = e - r * n; panel[r * ld + c] = Yp[(size_t)r * ldy + c]; }
-                    __syncthreads();
-                    for (int r = tid; r < rc; r += nt) {
-                        double *row = panel + r * ld;
-                        double dot = 0.0;
-                        for (int j = 0; j < n; ++j) {
-                            double s = row[j];
-                            for (int k = 0; k < j; ++k) s = fma(-row[k], bS[j * ld + k], s);
-                            s /= bS[j * ld + j];
-                            row[j] = s;
-                            dot = fma(s, sm_y[j], dot);
+                GPROF_T(5);
+                for (int e = tid; e < n * n; e += nt) { const int r = gen_div(e, mg_n), c = e - r * n; Ykk[(size_t)r * ldy + c] = bS[r * ld + c]; }
+                for (int c0 = 0; c0 < Rp; c0 += G.panel_rows) {
+                    const int rc = min(G.panel_rows, Rp - c0);
+                    double *Yp = Yp0 + (size_t)c0 * ldy;
+                    if (c0 > 0) {
+                        __syncthreads();
+#pragma unroll 4
+                        for (int e = tid; e < rc * ld; e += nt) {
+                            const int r = gen_div(e, mg_ld), c = e - r * ld;
+                            const double v = Yp[(size_t)r * ldy + min(c, n - 1)];
+                            panel[e] = (c < n) ? v : 0.0;
                         }
-                        yv[r0 + c0 + r] -= dot;                  // forward substitution rides along
+                        __syncthreads();
+                    }
+                    // in place, tile columns from the last to the first: tile column ct reads columns < 8 ct + 8 only
+                    for (int t8 = wid; 8 * t8 < rc; t8 += nw) {
+                        const int prow = 8 * t8 + gq;
+                        double *pr = panel + (size_t)min(prow, rc - 1) * ld;
+                        for (int ct = ntl - 1; ct >= 0; --ct) {
+                            const double *bl = bS + (size_t)(8 * ct + gq) * ld;
+                            const int ne = min(2 * (ct + 1), nks);
+                            double c0a = 0.0, c1a = 0.0, c0b = 0.0, c1b = 0.0;
+                            int ks = 0;
+                            for (; ks + 1 < ne; ks += 2) {
+                                dmma_gen(c0a, c1a, pr[4 * ks + q], bl[4 * ks + q]);
+                                dmma_gen(c0b, c1b, pr[4 * ks + 4 + q], bl[4 * ks + 4 + q]);
+                            }
+                            if (ks < ne) dmma_gen(c0a, c1a, pr[4 * ks + q], bl[4 * ks + q]);
+                            __syncwarp();
+                            const int c = 8 * ct + 2 * q;
+                            if (prow < rc) {
+                                if (c < n) pr[c] = c0a + c0b;
+                                if (c + 1 < n) pr[c + 1] = c1a + c1b;
+                            }
+                            __syncwarp();
+                        }
                     }
                     __syncthreads();
-                    for (int e = tid; e < rc * n; e += nt) { const int r = e / n, c = e - r * n; Yp[(size_t)r * ldy + c] = panel[r * ld + c]; }
+                    for (int e = tid; e < rc * n; e += nt) { const int r = gen_div(e, mg_n), c = e - r * n; Yp[(size_t)r * ldy + c] = panel[r * ld + c]; }
                 }
                 __syncthreads();
-                // trailing update  Y[r,c] -= sum_j P[r,j] P[c,j]   (r >= c), 4 x 4 register tiles
-                if (R > 0) {
-                    const double *P = whole ? panel : (Y + (size_t)r0 * ldy + (size_t)K * n);
-                    const size_t ldp = whole ? (size_t)ld : ldy;
-                    const int NT4 = (R + 3) / 4;
-                    const long long ntiles = (long long)NT4 * (NT4 + 1) / 2;
-                    for (long long e = tid; e < ntiles; e += nt) {
-                        int ti = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-                        while ((long long)(ti + 1) * (ti + 2) / 2 <= e) ++ti;
-                        while ((long long)ti * (ti + 1) / 2 > e) --ti;
-                        const int tj = (int)(e - (long long)ti * (ti + 1) / 2);
-                        const double *pa[4], *pb[4];
+                GPROF_T(6);
+                // trailing update: a warp per tile row, 4 tile columns at a time (4 independent chains), Y tiles read ahead of the products
+                auto trailing = [&](const double *P, const size_t ldp) {
+                    const int NT8 = (Rp + 7) >> 3;
+                    double *Yt = Y + (size_t)r0 * ldy + r0;
+                    auto load_y = [&](int ti, int tj0, double (&yo)[4][2]) {
+                        const int r = 8 * ti + gq, nact = min(4, ti - tj0 + 1);
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            pa[u] = P + (size_t)min(4 * ti + u, R - 1) * ldp;
-                            pb[u] = P + (size_t)min(4 * tj + u, R - 1) * ldp;
+                            const int c = 8 * (tj0 + u) + 2 * q;
+#pragma unroll
+                            for (int v = 0; v < 2; ++v)
+                                yo[u][v] = (u < nact && r < Rp && c + v <= r && c + v < R) ? Yt[(size_t)r * ldy + c + v] : 0.0;
                         }
-                        double acc[4][4];
+                    };
+                    // warp 0: the tile rows of the next diagonal block, then its factorisation (look-ahead); the others share the rest
+                    const int tstep = (wid == 0) ? 1 : nw - 1, tlim = (wid == 0) ? min(ntl, NT8) : NT8;
+                    int ti = (wid == 0) ? 0 : ntl + wid - 1, tj0 = 0;
+                    double yn[4][2];
+                    if (ti < tlim) load_y(ti, tj0, yn);
+                    while (ti < tlim) {
+                        double yo[4][2];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
+                        for (int u = 0; u < 4; ++u) { yo[u][0] = yn[u][0]; yo[u][1] = yn[u][1]; }
+                        int ti2 = ti, tj2 = tj0 + 4;                          // the group after this one: its Y tiles travel during the products
+                        if (tj2 > ti2) { ti2 += tstep; tj2 = 0; }
+                        if (ti2 < tlim) load_y(ti2, tj2, yn);
+                        const int r = 8 * ti + gq, nact = min(4, ti - tj0 + 1);
+                        const double *pa = P + (size_t)min(r, Rp - 1) * ldp;
+                        const double *pb[4];
+                        double acc[4][2];
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-                        for (int j = 0; j < n; ++j) {
-                            double av[4], bw[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) { av[u] = pa[u][j]; bw[u] = pb[u][j]; }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                                for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bw[v], acc[u][v]);
+                        for (int u = 0; u < 4; ++u) {
+                            pb[u] = P + (size_t)min(8 * (tj0 + u) + gq, Rp - 1) * ldp;
+                            acc[u][0] = acc[u][1] = 0.0;
                         }
+                        gen_chains_n<false>(nact, acc, pa, nullptr, pb, n, q);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = 8 * (tj0 + u) + 2 * q;
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                const int r = 4 * ti + u, c = 4 * tj + v;
-                                if (r < R && c <= r) Y[((size_t)(r0 + r)) * ldy + (size_t)(r0 + c)] -= acc[u][v];
-                            }
+                            for (int v = 0; v < 2; ++v)
+                                if (u < nact && r < Rp && c + v <= r && c + v < R) {
+                                    const double val = yo[u][v] - acc[u][v];
+                                    if (r < n) bS[r * ld + c + v] = val;              // the next diagonal block stays on chip (inv(L_KK) is dead)
+                                    else Yt[(size_t)r * ldy + c + v] = val;
+                                }
+                        }
+                        ti = ti2; tj0 = tj2;
                     }
+                    if (wid == 0) {
+                        __syncwarp();
+                        const int info = gen_potrf_dispatch(bS, n, ld, nrb, lane, sm_part, sm_y, sm_vec);
+                        if (lane == 0 && info) s_flag = info;
+                    }
+                };
+                if (R > 0) {                                                  // two instances: the shared-memory one uses shared loads
+                    if (whole) trailing(panel, (size_t)ld);
+                    else trailing(Yp0, ldy);
                 }
                 __syncthreads();
+                GPROF_T(7);
             }
             if (fail) { status = ST_NOT_PD; break; }
 
-            // ---- backward substitution  L' dnu = y  (:32) ----
+            // ---- backward substitution  L' dnu = y  (:32): dnu_K = inv(L_KK)' (y_K - sum_{r below} L[r, K]' dnu[r]) ----
+            const int parts = (8 * n <= nt) ? 8 : ((4 * n <= nt) ? 4 : ((2 * n <= nt) ? 2 : 1));     // lanes per entry of the inv(L_KK)' product
             for (int K = NB - 1; K >= 0; --K) {
                 const int r0 = (K + 1) * n;
-                {   // sm_vec[c] = y_K[c] - sum_{r >= r0} L[r, K n + c] dnu[r] : column dots split over nt / n row groups
-                    const int groups = max(1, nt / n);
-                    const int c = tid % n, g = tid / n;
-                    double s = 0.0;
-                    if (g < groups)
-                        for (int r = r0 + g; r < NE; r += groups) s = fma(Y[(size_t)r * ldy + (size_t)K * n + c], dnu[r], s);
-                    sm_part[tid] = (g < groups) ? s : 0.0;
-                    __syncthreads();
-                    for (int k = tid; k < n; k += nt) {
-                        double acc = yv[K * n + k];
-                        for (int gg = 0; gg < groups; ++gg) acc -= sm_part[gg * n + k];
-                        sm_vec[k] = acc;
-                    }
+                const int groups = max(1, nt / n);
+                const int c = tid % n, g = tid / n;
+                double s = 0.0;
+                if (g < groups) {
+                    const double *yc = Y + (size_t)K * n + c;
+#pragma unroll 8
+                    for (int r = r0 + g; r < NE; r += groups) s = fma(yc[(size_t)r * ldy], dnu[r], s);
+                }
+                sm_part[tid] = (g < groups) ? s : 0.0;
+                __syncthreads();
+                for (int k = tid; k < n; k += nt) {
+                    double acc = Y[(size_t)NE * ldy + (size_t)K * n + k];
+                    for (int gg = 0; gg < groups; ++gg) acc -= sm_part[gg * n + k];
+                    sm_vec[k] = acc;
                 }
                 __syncthreads();
-                if (wid == 0) {
-                    const double *Lf = Y + ((size_t)K * n) * ldy + (size_t)K * n;
-                    for (int j = n - 1; j >= 0; --j) {
-                        __syncwarp();
-                        const double xj = sm_vec[j] / Lf[(size_t)j * ldy + j];
-                        __syncwarp();
-                        if (lane == 0) sm_vec[j] = xj;
-                        for (int k = lane; k < j; k += 32) sm_vec[k] = fma(-Lf[(size_t)j * ldy + k], xj, sm_vec[k]);
-                    }
+                const double *Xd = Y + ((size_t)K * n) * ldy + (size_t)K * n;
+                for (int e0 = 0; e0 < n * parts; e0 += nt) {
+                    const int e = e0 + tid, k = e / parts, part = e - k * parts;
+                    double acc = 0.0;
+                    if (k < n)
+#pragma unroll 4
+                        for (int j = k + part; j < n; j += parts) acc = fma(Xd[(size_t)j * ldy + k], sm_vec[j], acc);
+                    for (int o = parts >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (k < n && part == 0) dnu[K * n + k] = acc;
                 }
-                __syncthreads();
-                for (int k = tid; k < n; k += nt) dnu[K * n + k] = sm_vec[k];
                 __syncthreads();
             }
 
+            GPROF_T(8);
             // ---- dz = inv(Phi)(-r_d - C' dnu)  (:34-35) ----
             gen_apply_Ct(G, NB, dnu, hd);
             __syncthreads();
@@ -546,15 +923,27 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             gen_apply_phi_inv(S, G, minv, zt, dz, -1.0);
             __syncthreads();
 
+            GPROF_T(9);
             // ---- backtracking on ||[r_p; r_d]||, d frozen (backtracking_inf_newton.m:2-11) ----
+            // The trial point and the window of C most block rows share live in shared memory for the whole search (the panel
+            // area is free): every trial re-reads both, and from the global scratch each pass waits on L2.
             double t = 1.0;
             int nh = 0;
+            const double *win_s = nullptr;
+            double *zts = zt;
+            if (G.ls_stage) {
+                int wl = 0;
+                for (int i = 0; i < NB; ++i) if (G.cw_ptr[i] == G.cw_main) wl = G.cw_len[i];
+                for (int e = tid; e < n * wl; e += nt) panel[e] = __ldg(G.cw + G.cw_main + e);
+                win_s = panel;
+                zts = panel + (size_t)n * wl;
+            }
             for (;;) {
-                for (int c = tid; c < N; c += nt) zt[c] = __fma_rn(t, dz[c], z[c]);
+                for (int c = tid; c < N; c += nt) zts[c] = __fma_rn(t, dz[c], z[c]);
                 __syncthreads();
-                gen_apply_C(G, NB, zt, bv, rpt);
+                gen_apply_C(G, NB, zts, bv, rpt, win_s, G.cw_main);
                 double sdt = 0.0;
-                for (int c = tid; c < N; c += nt) { const double r = gen_rd_elem(S, G, c, zt, __fma_rn(t, hd[c], h[c]), pd); sdt = fma(r, r, sdt); }
+                for (int c = tid; c < N; c += nt) { const double r = gen_rd_elem(S, G, c, zts, __fma_rn(t, hd[c], h[c]), pd); sdt = fma(r, r, sdt); }
                 __syncthreads();
                 double spt = 0.0;
                 for (int e = tid; e < NE; e += nt) spt = fma(rpt[e], rpt[e], spt);
@@ -568,7 +957,8 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
                 __syncthreads();
             }
             __syncthreads();
-            for (int c = tid; c < N; c += nt) { z[c] = zt[c]; h[c] = __fma_rn(t, hd[c], h[c]); }
+            GPROF_T(10);
+            for (int c = tid; c < N; c += nt) { z[c] = zts[c]; h[c] = __fma_rn(t, hd[c], h[c]); }
             for (int e = tid; e < NE; e += nt) { nu[e] = __fma_rn(t, dnu[e], nu[e]); rp[e] = rpt[e]; }
             ++iters;
             __syncthreads();
@@ -585,6 +975,11 @@ __global__ void __launch_bounds__(GEN_THREADS) fmpc_solve_kernel_gen(const DevSy
             if (A.iters) A.iters[b] = iters;
             atomicAdd(A.iters_total, (unsigned long long)iters);
         }
+        GPROF_T(11);
+#ifdef FMPC_PROF
+        if (A.prof && tid == 0)
+            for (int i_ = 0; i_ < 12; ++i_) atomicAdd((unsigned long long *)A.prof + i_, (unsigned long long)p_acc[i_]);
+#endif
     }
 }
 
@@ -636,7 +1031,7 @@ template <class T> T *gen_upload(std::vector<void *> &allocs, const std::vector<
     return (T *)p;
 }
 
-size_t gen_fixed_smem_doubles(int n) { return (size_t)n * (n | 1) + 2 * (size_t)n + GEN_THREADS + 34; }
+size_t gen_fixed_smem_doubles(int n) { const int n8 = (n + 7) & ~7, ld = gen_ld(n); return (size_t)(n8 > ld ? n8 : ld) * ld + 2 * (size_t)n + GEN_THREADS + 34; }
 
 } // namespace
 
@@ -778,6 +1173,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     GenSys G{};
     G.n = n; G.m = m; G.T = T; G.N = N; G.ramp = s->ramp_rows ? 1 : 0; G.ldyx = NE;
     G.dense_r = rdiag ? 0 : 1;
+    G.qdiag = qdiag ? 1 : 0;
     bool ok = true;
 #define GUP(field, vec) do { G.field = gen_upload(allocs, vec); if (!G.field) ok = false; } while (0)
     GUP(cw, cw); GUP(cw_ptr, cw_ptr); GUP(cw_off, cw_off); GUP(cw_len, cw_len);
@@ -792,12 +1188,12 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FMPC_ERR_CUDA;
-    const int ld = n | 1;
+    const int ld = gen_ld(n);
     const size_t fixed = gen_fixed_smem_doubles(n) * 8;
     const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 1024;
     if (fixed + 8 * (size_t)ld * 8 > budget) return FMPC_ERR_UNSUPPORTED;
     int prow = (int)((budget - fixed) / ((size_t)ld * 8));
-    if (prow > NE - n) prow = NE - n;
+    if (prow > NE - n + 1) prow = NE - n + 1;             // every row below the first block column + the right-hand-side row
     if (prow < 8) prow = 8;
     G.panel_rows = prow;
     size_t smem = fixed + (size_t)prow * ld * 8;
@@ -805,6 +1201,59 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
         const size_t need = fixed + (size_t)m * (m + 1) * 8;
         if (need > budget) return FMPC_ERR_UNSUPPORTED;
         if (need > smem) smem = need;
+    }
+    // Schur assembly: the u block most block rows reference (-B) is staged in the panel area when it fits
+    G.cu_main = -1;
+    if (!G.dense_r) {
+        int best = 0;
+        for (int i = 0; i < NBm; ++i)
+            for (int a = 0; a < ue_cnt[i]; ++a) {
+                int cnt = 0;
+                for (int k = 0; k < NBm; ++k) for (int b = 0; b < ue_cnt[k]; ++b) cnt += (ue_ptr[4 * k + b] == ue_ptr[4 * i + a]);
+                if (cnt > best) { best = cnt; G.cu_main = ue_ptr[4 * i + a]; }
+            }
+        const size_t need = fixed + (size_t)((n + 7) & ~7) * gen_ld(m) * 8;
+        if (need > budget) G.cu_main = -1;
+        else if (need > smem) smem = need;
+    }
+    {   // line search: the window most block rows share + the trial point in the panel area
+        int best = 0, wl = 0;
+        G.cw_main = -1;
+        for (int i = 0; i < NBm; ++i) {
+            int cnt = 0;
+            for (int k = 0; k < NBm; ++k) cnt += (cw_ptr[k] == cw_ptr[i]);
+            if (cnt > best) { best = cnt; G.cw_main = cw_ptr[i]; wl = cw_len[i]; }
+        }
+        const size_t need = fixed + ((size_t)n * wl + (size_t)N) * 8;
+        G.ls_stage = (G.cw_main >= 0 && need <= budget) ? 1 : 0;
+        if (G.ls_stage && need > smem) {
+            if (need <= smem + 16384) smem = need;               // a little more shared memory is fine, a lot would cost a resident CTA
+            else G.ls_stage = 0;
+        }
+    }
+    {   // Schur assembly tasks, most expensive first
+        const int ntl = ((n + 7) & ~7) >> 3, ngrp = (ntl + 3) >> 2;
+        std::vector<std::pair<int, int>> tk;                     // (-cost, task)
+        for (int i = 0, pr = 0; i < NBm; ++i)
+            for (int k = 0; k <= i; ++k, ++pr) {
+                const bool sym = ue_cnt[i] == 1 && ue_cnt[k] == 1 && ue_ptr[4 * i] == ue_ptr[4 * k] && (G.ramp || ue_t[4 * i] == ue_t[4 * k]);
+                int combos = 0;
+                for (int a = 0; a < ue_cnt[i]; ++a) for (int b = 0; b < ue_cnt[k]; ++b) combos += (G.ramp || ue_t[4 * i + a] == ue_t[4 * k + b]);
+                for (int rt = 0; rt < ntl; ++rt)
+                    for (int cg = 0; cg < ngrp; ++cg) {
+                        int nact = std::min(4, ntl - 4 * cg);
+                        if (sym) nact = std::min(nact, rt - 4 * cg + 1);
+                        if (nact <= 0) continue;
+                        const bool fast = (G.cu_main >= 0 && sym && ue_ptr[4 * i] == G.cu_main);       // both operands staged
+                        tk.push_back({-(combos * nact * (fast ? 2 : 3) + 1), (pr * ntl + rt) * ngrp + cg});
+                    }
+            }
+        std::sort(tk.begin(), tk.end());
+        std::vector<int> sch(tk.size());
+        for (size_t e = 0; e < tk.size(); ++e) sch[e] = tk[e].second;
+        G.nsch = (int)sch.size();
+        G.sch = gen_upload(allocs, sch);
+        if (!G.sch) return FMPC_ERR_CUDA;
     }
     if (cudaFuncSetAttribute(fmpc_solve_kernel_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FMPC_ERR_CUDA;
     int per_sm = 0;
@@ -823,6 +1272,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
 void fmpc_launch_solve_gen(const DevSys &S, const GenSys &G, const StepArgs &A, const SolveLaunchCfg &cfg, void *stream)
 {
     int grid = cfg.grid < A.nbatch ? cfg.grid : A.nbatch;
+    if (const char *e = getenv("FMPC_GEN_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }     // experiments: fewer resident CTAs
     if (grid < 1) grid = 1;
     fmpc_solve_kernel_gen<<<grid, cfg.block, cfg.smem, (cudaStream_t)stream>>>(S, G, A);
 }
