@@ -703,7 +703,11 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) fmpc_solve_kernel_g
                                 Cb[u] = sb ? panel + (size_t)cb * ldm : G.cu + pb + (size_t)min(cb, n - 1) * m;
                             }
                             const bool cvreg = cv && m <= 256 && (m & 3) == 0;
+#ifndef GEN_LDS      /* measured: shared-space loads here are 2.8 % SLOWER than generic ones (profiles/r02_gen_kernel_c1.log); opt-in */
+                            if (false) {
+#else
                             if (sa && sb && cvreg) {
+#endif
                                 // both operands are the staged block: pointers formed from the shared array directly, so that the
                                 // loads are shared-memory loads (a generic load is tracked like a global one and the products wait on it)
                                 const double *CaS = panel + (size_t)ra * ldm;
@@ -873,8 +877,12 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) fmpc_solve_kernel_g
                     }
                 };
                 if (R > 0) {                                                  // two instances: the shared-memory one uses shared loads
+#ifndef GEN_LDS
+                    trailing(whole ? panel : Yp0, whole ? (size_t)ld : ldy);
+#else
                     if (whole) trailing(panel, (size_t)ld);
                     else trailing(Yp0, ldy);
+#endif
                 }
                 __syncthreads();
                 GPROF_T(7);
