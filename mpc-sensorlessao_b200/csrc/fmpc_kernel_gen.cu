@@ -29,7 +29,8 @@ using namespace fmpc_dev;
 
 namespace {
 
-constexpr int GEN_THREADS = 256;
+constexpr int GEN_THREADS = 256;       // batches: 2 CTAs per SM
+constexpr int GEN_THREADS_WIDE = 512;  // fewer instances than SMs: one wide CTA per instance (every phase is spread over the warps at run time)
 #ifndef GEN_MIN_CTAS
 #define GEN_MIN_CTAS 2
 #endif
@@ -394,7 +395,8 @@ __device__ void gen_apply_phi_inv(const DevSys &S, const GenSys &G, const double
     }
 }
 
-__global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) fmpc_solve_kernel_gen(const DevSys S, const GenSys G, const StepArgs A)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc_solve_kernel_gen(const DevSys S, const GenSys G, const StepArgs A)
 {
     extern __shared__ double smem[];
     const int n = G.n, m = G.m, T = G.T, N = G.N, st = n + m;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(GEN_THREADS, GEN_MIN_CTAS) fmpc_solve_kernel_g
     double *sm_y = bS + (size_t)nrb * ld;               // n
     double *sm_vec = sm_y + n;                          // n
     double *sm_part = sm_vec + n;                       // nt
-    double *red = sm_part + nt;                         // 34
+    double *red = sm_part + GEN_THREADS_WIDE;           // 34  (one layout for both block sizes)
     double *panel = red + 34;                           // panel_rows x ld
     __shared__ int s_inst, s_flag, s_task;
 
@@ -1039,7 +1041,7 @@ template <class T> T *gen_upload(std::vector<void *> &allocs, const std::vector<
     return (T *)p;
 }
 
-size_t gen_fixed_smem_doubles(int n) { const int n8 = (n + 7) & ~7, ld = gen_ld(n); return (size_t)(n8 > ld ? n8 : ld) * ld + 2 * (size_t)n + GEN_THREADS + 34; }
+size_t gen_fixed_smem_doubles(int n) { const int n8 = (n + 7) & ~7, ld = gen_ld(n); return (size_t)(n8 > ld ? n8 : ld) * ld + 2 * (size_t)n + GEN_THREADS_WIDE + 34; }
 
 } // namespace
 
@@ -1263,9 +1265,10 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
         G.sch = gen_upload(allocs, sch);
         if (!G.sch) return FMPC_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(fmpc_solve_kernel_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FMPC_ERR_CUDA;
+    if (cudaFuncSetAttribute(fmpc_solve_kernel_gen<GEN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(fmpc_solve_kernel_gen<GEN_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FMPC_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_gen, GEN_THREADS, smem) != cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fmpc_solve_kernel_gen<GEN_THREADS>, GEN_THREADS, smem) != cudaSuccess || per_sm < 1)
         return FMPC_ERR_CUDA;
     cfg->grid = prop.multiProcessorCount * per_sm;
     cfg->block = GEN_THREADS;
@@ -1282,5 +1285,8 @@ void fmpc_launch_solve_gen(const DevSys &S, const GenSys &G, const StepArgs &A, 
     int grid = cfg.grid < A.nbatch ? cfg.grid : A.nbatch;
     if (const char *e = getenv("FMPC_GEN_GRID")) { const int g = atoi(e); if (g > 0 && g < grid) grid = g; }     // experiments: fewer resident CTAs
     if (grid < 1) grid = 1;
-    fmpc_solve_kernel_gen<<<grid, cfg.block, cfg.smem, (cudaStream_t)stream>>>(S, G, A);
+    // fewer instances than half the resident CTAs: every instance gets a 512-thread CTA of its own SM (single closed loops)
+    const bool wide = A.nbatch * 2 <= cfg.grid && !getenv("FMPC_GEN_NARROW");
+    if (wide) fmpc_solve_kernel_gen<GEN_THREADS_WIDE><<<grid, GEN_THREADS_WIDE, cfg.smem, (cudaStream_t)stream>>>(S, G, A);
+    else fmpc_solve_kernel_gen<GEN_THREADS><<<grid, cfg.block, cfg.smem, (cudaStream_t)stream>>>(S, G, A);
 }

@@ -57,8 +57,13 @@ GEN_CASES = [
 ]
 
 
+@pytest.mark.parametrize("block", ["wide", "narrow"])
 @pytest.mark.parametrize("cfg", GEN_CASES, ids=lambda g: f"s{g[0]}_n{g[1]}m{g[2]}T{g[3]}")
-def test_gen_kernel_matches_dense_oracle(pk, cfg):
+def test_gen_kernel_matches_dense_oracle(pk, cfg, block, monkeypatch):
+    """Both block sizes of the kernel: batches smaller than half the resident CTAs run one 512-thread CTA per instance,
+    larger ones 256-thread CTAs, two per SM (FMPC_GEN_NARROW=1 forces the latter)."""
+    if block == "narrow":
+        monkeypatch.setenv("FMPC_GEN_NARROW", "1")
     seed, n, m, T, nb, umax, du, xf, ramp, bug, dq = cfg
     c = var1_literal_case(seed, n, m, T, nb, umax, du, xf=xf, dense_q=dq)
     check_against_dense(pk, c, 5, 0.01, ramp, bug)
