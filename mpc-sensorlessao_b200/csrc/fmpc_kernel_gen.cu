@@ -29,7 +29,10 @@ using namespace fmpc_dev;
 
 namespace {
 
-constexpr int GEN_THREADS = 256;       // batches: 2 CTAs per SM
+#ifndef GEN_THREADS_N
+#define GEN_THREADS_N 256
+#endif
+constexpr int GEN_THREADS = GEN_THREADS_N;       // batches: GEN_MIN_CTAS CTAs per SM
 constexpr int GEN_THREADS_WIDE = 512;  // fewer instances than SMs: one wide CTA per instance (every phase is spread over the warps at run time)
 #ifndef GEN_MIN_CTAS
 #define GEN_MIN_CTAS 2
