@@ -78,48 +78,61 @@ __host__ __device__ __forceinline__ int gen_ld(int n) { int l = (n + 3) & ~3; if
 __device__ __forceinline__ unsigned gen_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }
 __device__ __forceinline__ int gen_div(int e, unsigned magic) { return (int)__umulhi((unsigned)e, magic); }
 
-// NACT accumulation chains sharing one A fragment: acc[u] += A(8 x K) B_u(8 x K)' over K columns, 4 per step.  Ca / Cb[u] point at
-// this lane's fragment row; the main loop is straight-line (no guards) so that the loads of the next steps are issued ahead of the
-// products; only a last partial step (K % 4) is guarded.  SCALE: the A fragment is scaled by cv (the diagonal of the middle factor).
-template <int NACT, bool SCALE>
-__device__ __forceinline__ void gen_chains(double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int q)
+// NR x NC accumulation chains: acc[r][u] += A_r(8 x K) B_u(8 x K)' over K columns, 4 per step -- NR + NC fragment loads feed NR * NC
+// tensor-pipe products (2 x 4: 0.75 loads per product).  Ca[r] / Cb[u] point at this lane's fragment row; the main loop is
+// straight-line (no guards) so that the loads of the next steps are issued ahead of the products; only a last partial step
+// (K % 4) is guarded.  SCALE: the A fragments are scaled by cv (the diagonal of the middle factor).
+template <int NR, int NC, bool SCALE>
+__device__ __forceinline__ void gen_chains(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q)
 {
     const int kf = K & ~3;
-#ifndef GEN_UNR
-#define GEN_UNR 2
-#endif
-    constexpr int unr = GEN_UNR;
-#pragma unroll unr
+#pragma unroll 2
     for (int jb = 0; jb < kf; jb += 4) {
         const int j = jb + q;
-        double av = Ca[j];
-        if (SCALE) av *= cv[j];
+        double av[NR];
 #pragma unroll
-        for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+        for (int r = 0; r < NR; ++r) av[r] = Ca[r][j];
+        if (SCALE) {
+            const double c = cv[j];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) av[r] *= c;
+        }
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+            const double bv = Cb[u][j];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) dmma_gen(acc[r][u][0], acc[r][u][1], av[r], bv);
+        }
     }
     if (kf < K) {
         const int j = kf + q;
         const bool ok = j < K;
-        double av = ok ? Ca[j] : 0.0;
-        if (SCALE) av *= ok ? cv[j] : 0.0;
+        const double c = SCALE ? (ok ? cv[j] : 0.0) : 1.0;
+        double av[NR];
 #pragma unroll
-        for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, ok ? Cb[u][j] : 0.0);
+        for (int r = 0; r < NR; ++r) av[r] = ok ? Ca[r][j] * c : 0.0;
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+            const double bv = ok ? Cb[u][j] : 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) dmma_gen(acc[r][u][0], acc[r][u][1], av[r], bv);
+        }
     }
 }
-template <bool SCALE>
-__device__ __forceinline__ void gen_chains_n(int nact, double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int q)
+template <int NR, bool SCALE>
+__device__ __forceinline__ void gen_chains_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q)
 {
-    if (nact == 4) gen_chains<4, SCALE>(acc, Ca, cv, Cb, K, q);
-    else if (nact == 3) gen_chains<3, SCALE>(acc, Ca, cv, Cb, K, q);
-    else if (nact == 2) gen_chains<2, SCALE>(acc, Ca, cv, Cb, K, q);
-    else gen_chains<1, SCALE>(acc, Ca, cv, Cb, K, q);
+    if (nc == 4) gen_chains<NR, 4, SCALE>(acc, Ca, cv, Cb, K, q);
+    else if (nc == 3) gen_chains<NR, 3, SCALE>(acc, Ca, cv, Cb, K, q);
+    else if (nc == 2) gen_chains<NR, 2, SCALE>(acc, Ca, cv, Cb, K, q);
+    else gen_chains<NR, 1, SCALE>(acc, Ca, cv, Cb, K, q);
 }
 
 // The SCALE chains with the diagonal cv (K <= 256 doubles, K % 4 == 0) read once, coalesced, into registers (lane l holds cv[32 b + l])
 // and handed to the k-steps by shuffles: the per-step cv load from the global scratch (L1 holds little next to the streaming Y)
 // was the top stall of the Schur assembly.
-template <int NACT>
-__device__ __forceinline__ void gen_chains_cv(double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int lane)
+template <int NR, int NC>
+__device__ __forceinline__ void gen_chains_cv(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane)
 {
     const int q = lane & 3;
     double cr[8];
@@ -131,32 +144,46 @@ __device__ __forceinline__ void gen_chains_cv(double (&acc)[4][2], const double 
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const int j = 32 * b + 4 * kk + q;
-                const double av = Ca[j] * __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
+                const double c = __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
+                double av[NR];
 #pragma unroll
-                for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+                for (int r = 0; r < NR; ++r) av[r] = Ca[r][j] * c;
+#pragma unroll
+                for (int u = 0; u < NC; ++u) {
+                    const double bv = Cb[u][j];
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) dmma_gen(acc[r][u][0], acc[r][u][1], av[r], bv);
+                }
             }
         } else if (32 * b < K) {
             const int kend = (K - 32 * b) >> 2;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                const bool on = kk < kend;                  // warp-uniform; off-steps multiply zeros (addresses stay inside the row)
+                const bool on = kk < kend;                  // warp-uniform; off-steps are skipped (addresses stay inside the row)
                 const int j = 32 * b + (on ? 4 * kk : 0) + q;
                 const double c = __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
-                const double av = on ? Ca[j] * c : 0.0;
                 if (on) {
+                    double av[NR];
 #pragma unroll
-                    for (int u = 0; u < NACT; ++u) dmma_gen(acc[u][0], acc[u][1], av, Cb[u][j]);
+                    for (int r = 0; r < NR; ++r) av[r] = Ca[r][j] * c;
+#pragma unroll
+                    for (int u = 0; u < NC; ++u) {
+                        const double bv = Cb[u][j];
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) dmma_gen(acc[r][u][0], acc[r][u][1], av[r], bv);
+                    }
                 }
             }
         }
     }
 }
-__device__ __forceinline__ void gen_chains_cv_n(int nact, double (&acc)[4][2], const double *Ca, const double *cv, const double *(&Cb)[4], int K, int lane)
+template <int NR>
+__device__ __forceinline__ void gen_chains_cv_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane)
 {
-    if (nact == 4) gen_chains_cv<4>(acc, Ca, cv, Cb, K, lane);
-    else if (nact == 3) gen_chains_cv<3>(acc, Ca, cv, Cb, K, lane);
-    else if (nact == 2) gen_chains_cv<2>(acc, Ca, cv, Cb, K, lane);
-    else gen_chains_cv<1>(acc, Ca, cv, Cb, K, lane);
+    if (nc == 4) gen_chains_cv<NR, 4>(acc, Ca, cv, Cb, K, lane);
+    else if (nc == 3) gen_chains_cv<NR, 3>(acc, Ca, cv, Cb, K, lane);
+    else if (nc == 2) gen_chains_cv<NR, 2>(acc, Ca, cv, Cb, K, lane);
+    else gen_chains_cv<NR, 1>(acc, Ca, cv, Cb, K, lane);
 }
 
 // In-place lower Cholesky of the n x n block Sm (leading dimension ld, lower triangle read), then in-place inverse of the factor:
@@ -645,7 +672,7 @@ __global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc
             // symmetric (diag(cv) is): only tiles on or below its diagonal are computed and mirrored.
             {
                 const int gq = lane >> 2, q = lane & 3;
-                const int ntl = n8 >> 3, ngrp = (ntl + 3) >> 2;
+                const int ntl = n8 >> 3, ngrp = (ntl + 3) >> 2, nrp = (ntl + 1) >> 1;
                 const int ldm = gen_ld(m);
                 const bool staged = G.cu_main >= 0;                       // host side: fits the panel area, diagonal R
                 if (staged) {
@@ -666,35 +693,40 @@ __global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc
                     slot = __shfl_sync(0xffffffffu, slot, 0);
                     if (slot >= G.nsch) break;
                     const int task = G.sch[slot];
-                    const int pr = task / (ntl * ngrp), tl = task - pr * ntl * ngrp, rt = tl / ngrp, ct0 = 4 * (tl - rt * ngrp);
+                    const int pr = task / (nrp * ngrp), tl = task - pr * nrp * ngrp, rp2 = tl / ngrp, ct0 = 4 * (tl - rp2 * ngrp);
                     int i = 0;
                     while ((i + 1) * (i + 2) / 2 <= pr) ++i;
                     const int k = pr - i * (i + 1) / 2;
                     if (i >= NB) continue;                                    // terminal block row of a problem solved without xf
                     const int na = G.ue_cnt[i], nbk = G.ue_cnt[k];
                     const bool sym = na == 1 && nbk == 1 && G.ue_ptr[4 * i] == G.ue_ptr[4 * k] && (G.ramp || G.ue_t[4 * i] == G.ue_t[4 * k]);
-                    int nact = min(4, ntl - ct0);
-                    if (sym) nact = min(nact, rt - ct0 + 1);
-                    if (nact <= 0) continue;                                  // the whole group lies above the diagonal of a symmetric block
-                    const int ra = 8 * rt + gq;
-                    // the products accumulate on top of the constant x part of the tile (read here, ahead of the chain); a mirrored
-                    // tile needs  Yx[c][r] - Yx[r][c]  on top of that
-                    double acc[4][2], dm[4][2];
+                    const int rt0 = 2 * rp2, nr = min(2, ntl - rt0);          // two tile rows x up to four tile columns per task
+                    int nc = min(4, ntl - ct0);
+                    if (sym) nc = min(nc, rt0 + nr - 1 - ct0 + 1);
+                    if (nc <= 0) continue;                                    // the whole group lies above the diagonal of a symmetric block
+                    // the products accumulate on top of the constant x part of the tiles (read here, ahead of the chains)
+                    double acc[2][4][2];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int ct = ct0 + u, c = 8 * ct + 2 * q;
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        const int ra = 8 * (rt0 + r2) + gq;
 #pragma unroll
-                        for (int v = 0; v < 2; ++v) {
-                            const bool on = u < nact && ra < n && c + v < n;
-                            acc[u][v] = on ? __ldg(G.Yx + ((size_t)i * n + ra) * G.ldyx + (size_t)k * n + c + v) : 0.0;
-                            dm[u][v] = (on && sym && ct < rt) ? __ldg(G.Yx + ((size_t)i * n + c + v) * G.ldyx + (size_t)k * n + ra) - acc[u][v] : 0.0;
+                        for (int u = 0; u < 4; ++u) {
+                            const int c = 8 * (ct0 + u) + 2 * q;
+#pragma unroll
+                            for (int v = 0; v < 2; ++v)
+                                acc[r2][u][v] = (r2 < nr && u < nc && ra < n && c + v < n) ? __ldg(G.Yx + ((size_t)i * n + ra) * G.ldyx + (size_t)k * n + c + v) : 0.0;
                         }
                     }
                     for (int a = 0; a < na; ++a) {
                         const int ta = G.ue_t[4 * i + a], pa = G.ue_ptr[4 * i + a];
                         const bool sa = staged && pa == G.cu_main;
-                        const double *Ca = G.dense_r ? Eb + ((size_t)i * 4 + a) * n * m + (size_t)min(ra, n - 1) * m
-                                         : sa ? panel + (size_t)ra * ldm : G.cu + pa + (size_t)min(ra, n - 1) * m;
+                        const double *Ca[2];
+#pragma unroll
+                        for (int r2 = 0; r2 < 2; ++r2) {
+                            const int ra = min(8 * (rt0 + min(r2, nr - 1)) + gq, n8 - 1);
+                            Ca[r2] = G.dense_r ? Eb + ((size_t)i * 4 + a) * n * m + (size_t)min(ra, n - 1) * m
+                                   : sa ? panel + (size_t)ra * ldm : G.cu + pa + (size_t)min(ra, n - 1) * m;
+                        }
                         for (int bb = 0; bb < nbk; ++bb) {
                             const int tb = G.ue_t[4 * k + bb], pb = G.ue_ptr[4 * k + bb];
                             if (!G.ramp && ta != tb) continue;
@@ -707,36 +739,29 @@ __global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc
                                 const int cb = min(8 * (ct0 + u) + gq, n8 - 1);
                                 Cb[u] = sb ? panel + (size_t)cb * ldm : G.cu + pb + (size_t)min(cb, n - 1) * m;
                             }
-                            const bool cvreg = cv && m <= 256 && (m & 3) == 0;
-#ifndef GEN_LDS      /* measured: shared-space loads here are 2.8 % SLOWER than generic ones (profiles/r02_gen_kernel_c1.log); opt-in */
-                            if (false) {
-#else
-                            if (sa && sb && cvreg) {
-#endif
-                                // both operands are the staged block: pointers formed from the shared array directly, so that the
-                                // loads are shared-memory loads (a generic load is tracked like a global one and the products wait on it)
-                                const double *CaS = panel + (size_t)ra * ldm;
-                                const double *CbS[4];
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) CbS[u] = panel + (size_t)min(8 * (ct0 + u) + gq, n8 - 1) * ldm;
-                                gen_chains_cv_n(nact, acc, CaS, cv, CbS, m, lane);
-                            } else if (cvreg) gen_chains_cv_n(nact, acc, Ca, cv, Cb, m, lane);
-                            else if (cv) gen_chains_n<true>(nact, acc, Ca, cv, Cb, m, q);
-                            else gen_chains_n<false>(nact, acc, Ca, cv, Cb, m, q);
+                            if (cv && m <= 256 && (m & 3) == 0) gen_chains_cv_n<2>(nc, acc, Ca, cv, Cb, m, lane);
+                            else if (cv) gen_chains_n<2, true>(nc, acc, Ca, cv, Cb, m, q);
+                            else gen_chains_n<2, false>(nc, acc, Ca, cv, Cb, m, q);
                         }
                     }
-                    const int r = 8 * rt + gq;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (u >= nact) continue;
-                        const int ct = ct0 + u, c = 8 * ct + 2 * q;
+                    for (int r2 = 0; r2 < 2; ++r2) {
+                        if (r2 >= nr) continue;
+                        const int rt = rt0 + r2, r = 8 * rt + gq;
                         if (r >= n) continue;
 #pragma unroll
-                        for (int v = 0; v < 2; ++v) {
-                            if (c + v >= n) continue;
-                            Y[((size_t)i * n + r) * ldy + (size_t)k * n + c + v] = acc[u][v];
-                            if (sym && ct < rt)                               // mirror inside the symmetric u part of the block
-                                Y[((size_t)i * n + c + v) * ldy + (size_t)k * n + r] = acc[u][v] + dm[u][v];
+                        for (int u = 0; u < 4; ++u) {
+                            if (u >= nc) continue;
+                            const int ct = ct0 + u, c = 8 * ct + 2 * q;
+                            if (sym && ct > rt) continue;                     // upper tile of a symmetric block: its mirror image is written below
+#pragma unroll
+                            for (int v = 0; v < 2; ++v) {
+                                if (c + v >= n) continue;
+                                Y[((size_t)i * n + r) * ldy + (size_t)k * n + c + v] = acc[r2][u][v];
+                                if (sym && ct < rt)                           // mirror inside the symmetric u part of the block
+                                    Y[((size_t)i * n + c + v) * ldy + (size_t)k * n + r] =
+                                        acc[r2][u][v] + __ldg(G.Yxd + ((size_t)i * n + r) * G.ldyx + (size_t)k * n + c + v);
+                            }
                         }
                     }
                 }
@@ -830,50 +855,49 @@ __global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc
                 auto trailing = [&](const double *P, const size_t ldp) {
                     const int NT8 = (Rp + 7) >> 3;
                     double *Yt = Y + (size_t)r0 * ldy + r0;
-                    auto load_y = [&](int ti, int tj0, double (&yo)[4][2]) {
-                        const int r = 8 * ti + gq, nact = min(4, ti - tj0 + 1);
+                    // a warp task: two tile rows x four tile columns (8 chains fed by 6 fragment loads per step); its Y tiles are read
+                    // ahead of the 56 products.  Warp 0 takes the row pairs of the next diagonal block, then factors it (look-ahead).
+                    const int NP2 = (NT8 + 1) >> 1, npl = (ntl + 1) >> 1;
+                    const int pstep = (wid == 0) ? 1 : nw - 1, plim = (wid == 0) ? min(npl, NP2) : NP2;
+                    for (int p2 = (wid == 0) ? 0 : npl + wid - 1; p2 < plim; p2 += pstep) {
+                        const int ti0 = 2 * p2, nr = min(2, NT8 - ti0), til = ti0 + nr - 1;
+                        const double *pa[2];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int c = 8 * (tj0 + u) + 2 * q;
+                        for (int r2 = 0; r2 < 2; ++r2) pa[r2] = P + (size_t)min(8 * (ti0 + min(r2, nr - 1)) + gq, Rp - 1) * ldp;
+                        for (int tj0 = 0; tj0 <= til; tj0 += 4) {
+                            const int nc = min(4, til - tj0 + 1);
+                            const double *pb[4];
+                            double acc[2][4][2], yo[2][4][2];
 #pragma unroll
-                            for (int v = 0; v < 2; ++v)
-                                yo[u][v] = (u < nact && r < Rp && c + v <= r && c + v < R) ? Yt[(size_t)r * ldy + c + v] : 0.0;
-                        }
-                    };
-                    // warp 0: the tile rows of the next diagonal block, then its factorisation (look-ahead); the others share the rest
-                    const int tstep = (wid == 0) ? 1 : nw - 1, tlim = (wid == 0) ? min(ntl, NT8) : NT8;
-                    int ti = (wid == 0) ? 0 : ntl + wid - 1, tj0 = 0;
-                    double yn[4][2];
-                    if (ti < tlim) load_y(ti, tj0, yn);
-                    while (ti < tlim) {
-                        double yo[4][2];
+                            for (int u = 0; u < 4; ++u) {
+                                pb[u] = P + (size_t)min(8 * (tj0 + u) + gq, Rp - 1) * ldp;
+                                const int c = 8 * (tj0 + u) + 2 * q;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { yo[u][0] = yn[u][0]; yo[u][1] = yn[u][1]; }
-                        int ti2 = ti, tj2 = tj0 + 4;                          // the group after this one: its Y tiles travel during the products
-                        if (tj2 > ti2) { ti2 += tstep; tj2 = 0; }
-                        if (ti2 < tlim) load_y(ti2, tj2, yn);
-                        const int r = 8 * ti + gq, nact = min(4, ti - tj0 + 1);
-                        const double *pa = P + (size_t)min(r, Rp - 1) * ldp;
-                        const double *pb[4];
-                        double acc[4][2];
+                                for (int r2 = 0; r2 < 2; ++r2) {
+                                    const int r = 8 * (ti0 + r2) + gq;
+                                    acc[r2][u][0] = acc[r2][u][1] = 0.0;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            pb[u] = P + (size_t)min(8 * (tj0 + u) + gq, Rp - 1) * ldp;
-                            acc[u][0] = acc[u][1] = 0.0;
-                        }
-                        gen_chains_n<false>(nact, acc, pa, nullptr, pb, n, q);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int c = 8 * (tj0 + u) + 2 * q;
-#pragma unroll
-                            for (int v = 0; v < 2; ++v)
-                                if (u < nact && r < Rp && c + v <= r && c + v < R) {
-                                    const double val = yo[u][v] - acc[u][v];
-                                    if (r < n) bS[r * ld + c + v] = val;              // the next diagonal block stays on chip (inv(L_KK) is dead)
-                                    else Yt[(size_t)r * ldy + c + v] = val;
+                                    for (int v = 0; v < 2; ++v)
+                                        yo[r2][u][v] = (r2 < nr && u < nc && r < Rp && c + v <= r && c + v < R) ? Yt[(size_t)r * ldy + c + v] : 0.0;
                                 }
+                            }
+                            gen_chains_n<2, false>(nc, acc, pa, nullptr, pb, n, q);
+#pragma unroll
+                            for (int r2 = 0; r2 < 2; ++r2) {
+                                const int r = 8 * (ti0 + r2) + gq;
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    const int c = 8 * (tj0 + u) + 2 * q;
+#pragma unroll
+                                    for (int v = 0; v < 2; ++v)
+                                        if (r2 < nr && u < nc && r < Rp && c + v <= r && c + v < R) {
+                                            const double val = yo[r2][u][v] - acc[r2][u][v];
+                                            if (r < n) bS[r * ld + c + v] = val;          // the next diagonal block stays on chip (inv(L_KK) is dead)
+                                            else Yt[(size_t)r * ldy + c + v] = val;
+                                        }
+                                }
+                            }
                         }
-                        ti = ti2; tj0 = tj2;
                     }
                     if (wid == 0) {
                         __syncwarp();
@@ -1244,21 +1268,22 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
             else G.ls_stage = 0;
         }
     }
-    {   // Schur assembly tasks, most expensive first
-        const int ntl = ((n + 7) & ~7) >> 3, ngrp = (ntl + 3) >> 2;
+    {   // Schur assembly tasks (pair, two tile rows, four tile columns), most expensive first
+        const int ntl = ((n + 7) & ~7) >> 3, ngrp = (ntl + 3) >> 2, nrp = (ntl + 1) >> 1;
         std::vector<std::pair<int, int>> tk;                     // (-cost, task)
         for (int i = 0, pr = 0; i < NBm; ++i)
             for (int k = 0; k <= i; ++k, ++pr) {
                 const bool sym = ue_cnt[i] == 1 && ue_cnt[k] == 1 && ue_ptr[4 * i] == ue_ptr[4 * k] && (G.ramp || ue_t[4 * i] == ue_t[4 * k]);
                 int combos = 0;
                 for (int a = 0; a < ue_cnt[i]; ++a) for (int b = 0; b < ue_cnt[k]; ++b) combos += (G.ramp || ue_t[4 * i + a] == ue_t[4 * k + b]);
-                for (int rt = 0; rt < ntl; ++rt)
+                for (int rp = 0; rp < nrp; ++rp)
                     for (int cg = 0; cg < ngrp; ++cg) {
-                        int nact = std::min(4, ntl - 4 * cg);
-                        if (sym) nact = std::min(nact, rt - 4 * cg + 1);
-                        if (nact <= 0) continue;
+                        const int nr = std::min(2, ntl - 2 * rp);
+                        int nc = std::min(4, ntl - 4 * cg);
+                        if (sym) nc = std::min(nc, 2 * rp + nr - 4 * cg);
+                        if (nc <= 0) continue;
                         const bool fast = (G.cu_main >= 0 && sym && ue_ptr[4 * i] == G.cu_main);       // both operands staged
-                        tk.push_back({-(combos * nact * (fast ? 2 : 3) + 1), (pr * ntl + rt) * ngrp + cg});
+                        tk.push_back({-(combos * nc * (fast ? 2 : 3) + 1), (pr * nrp + rp) * ngrp + cg});
                     }
             }
         std::sort(tk.begin(), tk.end());
@@ -1267,6 +1292,14 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
         G.nsch = (int)sch.size();
         G.sch = gen_upload(allocs, sch);
         if (!G.sch) return FMPC_ERR_CUDA;
+        std::vector<double> Yxd((size_t)NE * NE, 0.0);           // per block: transpose minus the block
+        for (int i = 0; i < NBm; ++i)
+            for (int k = 0; k < NBm; ++k)
+                for (int r = 0; r < n; ++r)
+                    for (int c = 0; c < n; ++c)
+                        Yxd[(size_t)(i * n + r) * NE + (size_t)k * n + c] = Yx[(size_t)(i * n + c) * NE + (size_t)k * n + r] - Yx[(size_t)(i * n + r) * NE + (size_t)k * n + c];
+        G.Yxd = gen_upload(allocs, Yxd);
+        if (!G.Yxd) return FMPC_ERR_CUDA;
     }
     if (cudaFuncSetAttribute(fmpc_solve_kernel_gen<GEN_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(fmpc_solve_kernel_gen<GEN_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return FMPC_ERR_CUDA;
