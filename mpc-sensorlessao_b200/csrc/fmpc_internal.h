@@ -87,6 +87,7 @@ struct GenSys {
     const int *cw_ptr, *cw_off, *cw_len;    // per block row (T+1): offset into cw, first column, width
     const double *cu, *cut;                 // pool of n x m blocks C[i, u_t] (row-major) and their transposes (m x n)
     const int *ue_cnt, *ue_t, *ue_ptr;      // per block row: number of u blocks (<= 4), their stages, offsets into cu
+    const int *ue_lo, *ue_hi;               // per (block row, u block): the columns [lo, hi) of the block that are not all zero (multiples of 4)
     const double *Yx;                       // ((T+1) n)^2 row-major: C_x inv(Phi_xx) C_x'
     const double *Yxd;                      // same layout: per n x n block, transpose minus the block (what a mirrored Schur tile adds)
     const double *Q2, *Q2f, *Qi, *Qif;      // n x n row-major: 2Q, 2Qf and their inverses

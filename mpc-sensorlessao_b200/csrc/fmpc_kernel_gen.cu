@@ -83,11 +83,11 @@ __device__ __forceinline__ int gen_div(int e, unsigned magic) { return (int)__um
 // straight-line (no guards) so that the loads of the next steps are issued ahead of the products; only a last partial step
 // (K % 4) is guarded.  SCALE: the A fragments are scaled by cv (the diagonal of the middle factor).
 template <int NR, int NC, bool SCALE>
-__device__ __forceinline__ void gen_chains(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q)
+__device__ __forceinline__ void gen_chains(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q, int k0 = 0)
 {
-    const int kf = K & ~3;
+    const int kf = K & ~3;                                  // columns [k0, K), k0 a multiple of 4
 #pragma unroll 2
-    for (int jb = 0; jb < kf; jb += 4) {
+    for (int jb = k0; jb < kf; jb += 4) {
         const int j = jb + q;
         double av[NR];
 #pragma unroll
@@ -120,27 +120,29 @@ __device__ __forceinline__ void gen_chains(double (&acc)[2][4][2], const double 
     }
 }
 template <int NR, bool SCALE>
-__device__ __forceinline__ void gen_chains_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q)
+__device__ __forceinline__ void gen_chains_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int q, int k0 = 0)
 {
-    if (nc == 4) gen_chains<NR, 4, SCALE>(acc, Ca, cv, Cb, K, q);
-    else if (nc == 3) gen_chains<NR, 3, SCALE>(acc, Ca, cv, Cb, K, q);
-    else if (nc == 2) gen_chains<NR, 2, SCALE>(acc, Ca, cv, Cb, K, q);
-    else gen_chains<NR, 1, SCALE>(acc, Ca, cv, Cb, K, q);
+    if (nc == 4) gen_chains<NR, 4, SCALE>(acc, Ca, cv, Cb, K, q, k0);
+    else if (nc == 3) gen_chains<NR, 3, SCALE>(acc, Ca, cv, Cb, K, q, k0);
+    else if (nc == 2) gen_chains<NR, 2, SCALE>(acc, Ca, cv, Cb, K, q, k0);
+    else gen_chains<NR, 1, SCALE>(acc, Ca, cv, Cb, K, q, k0);
 }
 
 // The SCALE chains with the diagonal cv (K <= 256 doubles, K % 4 == 0) read once, coalesced, into registers (lane l holds cv[32 b + l])
 // and handed to the k-steps by shuffles: the per-step cv load from the global scratch (L1 holds little next to the streaming Y)
 // was the top stall of the Schur assembly.
 template <int NR, int NC>
-__device__ __forceinline__ void gen_chains_cv(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane)
+__device__ __forceinline__ void gen_chains_cv(double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane,
+                                              int k0, int k1)
 {
+    // columns [k0, k1) only (multiples of 4): the operand blocks of the literal VAR_1 second row are zero outside a column range
     const int q = lane & 3;
     double cr[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) cr[b] = (32 * b + lane < K) ? cv[32 * b + lane] : 0.0;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-        if (32 * b + 32 <= K) {                             // a whole block of 8 k-steps: straight-line, the loads run ahead of the products
+        if (32 * b >= k0 && 32 * b + 32 <= k1) {            // a whole block of 8 k-steps: straight-line, the loads run ahead of the products
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
                 const int j = 32 * b + 4 * kk + q;
@@ -155,12 +157,12 @@ __device__ __forceinline__ void gen_chains_cv(double (&acc)[2][4][2], const doub
                     for (int r = 0; r < NR; ++r) dmma_gen(acc[r][u][0], acc[r][u][1], av[r], bv);
                 }
             }
-        } else if (32 * b < K) {
-            const int kend = (K - 32 * b) >> 2;
+        } else if (32 * b < k1 && 32 * b + 32 > k0) {
+            const int kbeg = max(0, (k0 - 32 * b) >> 2), kend = min(8, (k1 - 32 * b) >> 2);
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                const bool on = kk < kend;                  // warp-uniform; off-steps are skipped (addresses stay inside the row)
-                const int j = 32 * b + (on ? 4 * kk : 0) + q;
+                const bool on = kk >= kbeg && kk < kend;    // warp-uniform; off-steps are skipped (addresses stay inside the row)
+                const int j = 32 * b + (on ? 4 * kk : 4 * kbeg) + q;
                 const double c = __shfl_sync(0xffffffffu, cr[b], 4 * kk + q);
                 if (on) {
                     double av[NR];
@@ -178,12 +180,13 @@ __device__ __forceinline__ void gen_chains_cv(double (&acc)[2][4][2], const doub
     }
 }
 template <int NR>
-__device__ __forceinline__ void gen_chains_cv_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane)
+__device__ __forceinline__ void gen_chains_cv_n(int nc, double (&acc)[2][4][2], const double *(&Ca)[2], const double *cv, const double *(&Cb)[4], int K, int lane,
+                                                int k0, int k1)
 {
-    if (nc == 4) gen_chains_cv<NR, 4>(acc, Ca, cv, Cb, K, lane);
-    else if (nc == 3) gen_chains_cv<NR, 3>(acc, Ca, cv, Cb, K, lane);
-    else if (nc == 2) gen_chains_cv<NR, 2>(acc, Ca, cv, Cb, K, lane);
-    else gen_chains_cv<NR, 1>(acc, Ca, cv, Cb, K, lane);
+    if (nc == 4) gen_chains_cv<NR, 4>(acc, Ca, cv, Cb, K, lane, k0, k1);
+    else if (nc == 3) gen_chains_cv<NR, 3>(acc, Ca, cv, Cb, K, lane, k0, k1);
+    else if (nc == 2) gen_chains_cv<NR, 2>(acc, Ca, cv, Cb, K, lane, k0, k1);
+    else gen_chains_cv<NR, 1>(acc, Ca, cv, Cb, K, lane, k0, k1);
 }
 
 // In-place lower Cholesky of the n x n block Sm (leading dimension ld, lower triangle read), then in-place inverse of the factor:
@@ -739,9 +742,14 @@ __global__ void __launch_bounds__(NT, NT == GEN_THREADS ? GEN_MIN_CTAS : 1) fmpc
                                 const int cb = min(8 * (ct0 + u) + gq, n8 - 1);
                                 Cb[u] = sb ? panel + (size_t)cb * ldm : G.cu + pb + (size_t)min(cb, n - 1) * m;
                             }
-                            if (cv && m <= 256 && (m & 3) == 0) gen_chains_cv_n<2>(nc, acc, Ca, cv, Cb, m, lane);
-                            else if (cv) gen_chains_n<2, true>(nc, acc, Ca, cv, Cb, m, q);
-                            else gen_chains_n<2, false>(nc, acc, Ca, cv, Cb, m, q);
+                            // columns where both blocks have entries (the blocks of the literal second row are zero outside a range);
+                            // dense R: the A operand is E = C_a inv(Phi_uu), dense in every column
+                            const int k0 = G.dense_r ? G.ue_lo[4 * k + bb] : max(G.ue_lo[4 * i + a], G.ue_lo[4 * k + bb]);
+                            const int k1 = G.dense_r ? G.ue_hi[4 * k + bb] : min(G.ue_hi[4 * i + a], G.ue_hi[4 * k + bb]);
+                            if (k0 >= k1) continue;
+                            if (cv && m <= 256 && (m & 3) == 0) gen_chains_cv_n<2>(nc, acc, Ca, cv, Cb, m, lane, k0, k1);
+                            else if (cv) gen_chains_n<2, true>(nc, acc, Ca, cv, Cb, min(k1, m), q, k0);
+                            else gen_chains_n<2, false>(nc, acc, Ca, cv, Cb, min(k1, m), q, k0);
                         }
                     }
 #pragma unroll
@@ -1129,7 +1137,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     }
     // ---- u-column blocks per block row: stages whose u columns this row touches ----
     std::vector<double> cu, cut;
-    std::vector<int> ue_cnt(NBm, 0), ue_t(4 * NBm, 0), ue_ptr(4 * NBm, 0);
+    std::vector<int> ue_cnt(NBm, 0), ue_t(4 * NBm, 0), ue_ptr(4 * NBm, 0), ue_lo(4 * NBm, 0), ue_hi(4 * NBm, 0);
     for (int i = 0; i < NBm; ++i)
         for (int t = 0; t < T; ++t) {
             std::vector<double> blk((size_t)n * m);
@@ -1147,6 +1155,10 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
                 cut.resize(cu.size());
                 for (int r = 0; r < n; ++r) for (int j = 0; j < m; ++j) cut[(size_t)found + (size_t)j * n + r] = blk[(size_t)r * m + j];
             }
+            int jlo = m, jhi = 0;                                 // non-zero column range, widened to multiples of 4
+            for (int r = 0; r < n; ++r)
+                for (int j = 0; j < m; ++j) if (blk[(size_t)r * m + j] != 0.0) { jlo = std::min(jlo, j); jhi = std::max(jhi, j + 1); }
+            ue_lo[4 * i + ue_cnt[i]] = jlo & ~3; ue_hi[4 * i + ue_cnt[i]] = std::min((jhi + 3) & ~3, (m + 3) & ~3);
             ue_t[4 * i + ue_cnt[i]] = t; ue_ptr[4 * i + ue_cnt[i]] = found; ++ue_cnt[i];
         }
     // ---- dense 2Q, 2Qf and their inverses (row-major) ----
@@ -1214,7 +1226,7 @@ int fmpc_gen_create(const fmpc_sys *s, int device, GenSys *out, std::vector<void
     bool ok = true;
 #define GUP(field, vec) do { G.field = gen_upload(allocs, vec); if (!G.field) ok = false; } while (0)
     GUP(cw, cw); GUP(cw_ptr, cw_ptr); GUP(cw_off, cw_off); GUP(cw_len, cw_len);
-    GUP(cu, cu); GUP(cut, cut); GUP(ue_cnt, ue_cnt); GUP(ue_t, ue_t); GUP(ue_ptr, ue_ptr);
+    GUP(cu, cu); GUP(cut, cut); GUP(ue_cnt, ue_cnt); GUP(ue_t, ue_t); GUP(ue_ptr, ue_ptr); GUP(ue_lo, ue_lo); GUP(ue_hi, ue_hi);
     GUP(Yx, Yx); GUP(Q2, Q2); GUP(Q2f, Q2f); GUP(Qi, Qi); GUP(Qif, Qif);
     std::vector<double> dumin(m, 0.0), dumax(m, 0.0);
     if (s->ramp_rows) { dumin.assign(s->du_min, s->du_min + m); dumax.assign(s->du_max, s->du_max + m); }
