@@ -13,3 +13,7 @@ $S --tool memcheck python -m pytest tests/test_gpu_fmpc.py tests/test_gpu_multi.
 $S --tool racecheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "stream_on_device or resident_steps" 2>&1 | tail -4
 $S --tool memcheck python -m pytest tests/test_gpu_fmpc_gen.py tests/test_gpu_zernike.py tests/test_gpu_estimator.py -m gpu -x -q -k "s401 or s403 or s404 or 500-4 or 257-10 or other_shapes" 2>&1 | tail -4
 $S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s401 or s403" 2>&1 | tail -4
+# general-structure kernel after the round-2 rewrite: both block sizes, n > 32 (shared-memory potrf), dense R, chunked panel (n = 100)
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s301 or s304 or s306 or s308 or s309 or s310 or cold_start or s401 or s403" 2>&1 | tail -4
+$S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s310 or s305 or s304 or s401" 2>&1 | tail -4
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "72 or no_size_limit or larger" 2>&1 | tail -4
