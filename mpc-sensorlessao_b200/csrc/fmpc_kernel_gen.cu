@@ -10,10 +10,14 @@
 //   * dense (non-diagonal) SPD Q / Qf: inv(2Q) is a dense constant, the x part of Y is precomputed on the host.
 // One persistent CTA per MPC instance (dynamic instance counter), same Newton / early-exit / back-tracking control
 // flow as the other kernels (inf_newton_solver.m:10-41, backtracking_inf_newton.m:2-11).  Per iteration:
-//   barrier terms -> residuals -> per-actuator tridiagonal LDL' + explicit inverse M_j (T x T) ->
-//   Y = Yx + sum Cu_a diag(M[t_a,t_b,:]) Cu_b'  -> dense blocked Cholesky (n x n diagonal blocks in shared memory,
-//   panel in shared memory, 4 x 4 register tiles for the trailing update) fused with the forward substitution ->
-//   backward substitution -> dz = inv(Phi)(-r_d - C' dnu) -> residual-norm back-tracking.
+//   barrier terms -> residuals -> per-actuator tridiagonal LDL' + explicit inverse M_j (T x T, by recurrences) ->
+//   Y = Yx + sum Cu_a diag(M[t_a,t_b,:]) Cu_b'  (warp tasks of 2 x 4 DMMA tiles, -B staged in shared memory) ->
+//   dense blocked Cholesky with the right-hand side as one more row: inv(L_KK) by one warp (registers, look-ahead: it
+//   runs during the trailing update of the block column before), panel <- panel inv(L_KK)' and the trailing update as DMMA
+//   tiles from shared memory -> backward substitution (products with inv(L_KK)') -> dz = inv(Phi)(-r_d - C' dnu) ->
+//   residual-norm back-tracking (window of C + trial point in shared memory).
+// Two block sizes: 256 threads (two CTAs per SM) for batches, 512 threads per instance for batches below half the resident
+// CTAs (FMPC_GEN_NARROW=1 forces 256; FMPC_GEN_GRID=g caps the resident CTAs: experiments).  DESIGN.md 3a has the numbers.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cstring>
