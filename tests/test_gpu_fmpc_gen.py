@@ -108,6 +108,33 @@ def test_gen_kernel_matches_golden(pk, path):
     assert np.array_equal(out["iters"], c["iters"])
 
 
+@pytest.mark.parametrize("block", ["wide", "narrow"])
+def test_gen_batch_at_c1_size_matches_golden(pk, block, monkeypatch):
+    """The C1-size fixture (n = 27, m = 144, T = 10, ramp rows + literal C) replicated to a batch larger than the resident CTAs:
+    persistent 256-thread CTAs (two per SM, dynamic instance counter) on a full machine, and -- with a batch below half the
+    resident CTAs -- the 512-thread CTA per instance.  Every copy has to reproduce the golden solution."""
+    path = os.path.join(GOLD, "var1lit_readme_c1_n27_T10.npz")
+    g = np.load(path)
+    c = {k: g[k] for k in g.files}
+    for k in ("n", "m", "T", "nb", "niters"):
+        c[k] = int(c[k])
+    for k in ("A2", "x0_pre", "xf"):
+        c.setdefault(k, None)
+    reps = 700 // c["nb"] if block == "narrow" else max(1, 8 // c["nb"])
+    if block == "narrow" and reps * c["nb"] < 600:
+        pytest.skip("fixture too small to fill the machine")
+    big = dict(c)
+    for k in ("x0", "x0_pre", "w", "xf", "X0", "U0", "nu0", "u_prev"):
+        if c.get(k) is not None:
+            big[k] = np.ascontiguousarray(np.concatenate([c[k]] * reps, axis=0))
+    big["nb"] = reps * c["nb"]
+    out = gen_solve(pk, big, c["niters"], float(c["kappa"]), bool(c["ramp"]), bool(c["bug"]))
+    for b in range(big["nb"]):
+        o = b % c["nb"]
+        assert relerr(out["U"][b], c["U"][o]) < TOL and relerr(out["X"][b], c["X"][o]) < TOL, f"copy {b}"
+    assert np.array_equal(out["iters"], np.tile(c["iters"], reps))
+
+
 def test_var1_class_is_the_reference_by_default(pk):
     """Fast_MPC2_VAR1 with the reference's 21 ctor arguments = ramp rows + literal C (VAR_1/Fast_MPC2.m:26-51)."""
     from oracle import fastmpc_dense as fd
