@@ -153,12 +153,12 @@ struct WGeom {
         g.TP8 = 8 * g.NTT;
         g.NN = g.NPOT * g.NPOT;
         g.WB = 2 * g.mpad + 128;                       // two staged w rows + the stash of the paired last tile row (forward_sweep)
-        if (g.WB < 128) g.WB = 128;                    // also holds the 4 x 32 vectors of the backward sweep
+        if (g.WB < 160) g.WB = 160;                    // also holds the 5 x 32 vectors of the backward sweep
         //          B            A1, A2                umax umin r2 rl     q2 q2f ql qfl qi qif
         g.const_doubles = (size_t)n * g.LDB + 2 * ((size_t)n * g.LD) + 4 * (size_t)g.mpad + 6 * (size_t)g.npad;
         g.const_doubles = (g.const_doubles + 1) & ~(size_t)1;
         g.warp_doubles = 3 * (size_t)g.BLK + (size_t)g.WB;
-        if (g.warp_doubles < 3 * (size_t)g.NN + 128) g.warp_doubles = 3 * (size_t)g.NN + 128;   // backward ring: 3 slots of NN + vectors
+        if (g.warp_doubles < 3 * (size_t)g.NN + 160) g.warp_doubles = 3 * (size_t)g.NN + 160;   // backward ring: 3 slots of NN + 5 x 32 vectors
         if (g.warp_doubles < 2400) g.warp_doubles = 2400;                                   // u-space stream ring of the passes
         g.tail_doubles = 8 * (size_t)g.LD + 8;   // overrun reads of the last rows stay inside the allocation
         return g;
@@ -241,7 +241,6 @@ struct WCtx {
     __device__ __forceinline__ double *BV() const { return ba(4); }
     __device__ __forceinline__ double *gLi() const { return fa(0); }
     __device__ __forceinline__ double *gL1() const { return fa(1); }
-    __device__ __forceinline__ double *gL2() const { return fa(2); }
 };
 
 // K_NORM: the residual norms of K_NEWTON (same expressions, same summation order) without its GEMM and scratch stores.
@@ -1150,8 +1149,7 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
         }
         if (has2) {
             const bool y2ok = (c.y2i[i] >= 0);
-            double *g = c.gL2() + (size_t)i * (NPOT * NPOT) + gq * NPOT + 2 * q;
-            double *s = bL2pp + gq * LD + 2 * q;
+            double *s = bL2pp + gq * LD + 2 * q;             // L2_i stays on chip: the backward sweep rebuilds L2_i' v from inv(L_i) and Y2
             double nqi[CT][2];                                // -inv(2Q)(k) for k = 8 jt + 2 q + e  (0 for k >= n)
 #pragma unroll
             for (int jt = 0; jt < CT; ++jt) {
@@ -1176,7 +1174,6 @@ __device__ __forceinline__ int forward_sweep(const WCtx &c PROF_PARAMS)
                     const bool c0 = (ct < CT - 1) || cok0, c1 = (ct < CT - 1) || cok1;
                     if (rok && c0) s[8 * rt * LD + 8 * ct] = o[0];
                     if (rok && c1) s[8 * rt * LD + 8 * ct + 1] = o[1];
-                    if (rok && c0) *reinterpret_cast<double2 *>(g + 8 * rt * NPOT + 8 * ct) = make_double2(o[0], o[1]);
                 }
             }
             if (yrow) {                                       // row n of the L2 block carries y_i as well
@@ -1206,10 +1203,10 @@ template <int NPOT>
 __device__ __forceinline__ void ring_issue(const WCtx &c, const int e, const int nent)
 {
     if (e < nent) {
-        const int i = c.NB - 1 - e / 3, kind = e % 3;
-        const bool on = (kind == 2) || (kind == 0 && i + 1 < c.NB) || (kind == 1 && i + 2 < c.NB && c.a2);
+        const int i = c.NB - 1 - e / 2, kind = e % 2;        // per stage: L1_i (kind 0), inv(L_i) (kind 1)
+        const bool on = (kind == 1) || (i + 1 < c.NB);
         if (on) {
-            const double *src = (kind == 0 ? c.gL1() : (kind == 1 ? c.gL2() : c.gLi())) + (size_t)i * (NPOT * NPOT);
+            const double *src = (kind == 0 ? c.gL1() : c.gLi()) + (size_t)i * (NPOT * NPOT);
             double *dst = c.wsm + (e % 3) * (NPOT * NPOT);
             for (int ch = c.lane; ch < NPOT * NPOT / 2; ch += 32) cp_async16(dst + 2 * ch, src + 2 * ch);
         }
@@ -1217,29 +1214,32 @@ __device__ __forceinline__ void ring_issue(const WCtx &c, const int e, const int
     cp_async_commit();
 }
 
+// L2_i = Y2 inv(L_i)' is not read back (nor stored: a third of the factor scratch traffic): L2_i' v = inv(L_i) (Y2' v) with
+// Y2 = -A2 inv(2Q) from the constants in shared memory and inv(L_i), which the stage needs anyway.
 template <int NPOT>
 __device__ __forceinline__ void backward_sweep(const WCtx &c)
 {
-    constexpr int npad = 8 * ((NPOT + 7) / 8);
+    constexpr int npad = 8 * ((NPOT + 7) / 8), LD = (NPOT % 8 == 4) ? NPOT : NPOT + 4;
     const int n = c.n, NB = c.NB, lane = c.lane;
-    double *vec = c.wsm + 3 * (NPOT * NPOT);                 // [3][32] dnu ring + [32] tmp (behind the 3 ring slots)
-    const int nent = 3 * NB;
+    double *vec = c.wsm + 3 * (NPOT * NPOT);                 // [3][32] dnu ring + [32] tmp + [32] Y2' dnu (behind the 3 ring slots)
+    const int nent = 2 * NB;
     const bool act = lane < n;
     __syncwarp();
-    vec[lane] = 0.0; vec[32 + lane] = 0.0; vec[64 + lane] = 0.0; vec[96 + lane] = 0.0;
+    vec[lane] = 0.0; vec[32 + lane] = 0.0; vec[64 + lane] = 0.0; vec[96 + lane] = 0.0; vec[128 + lane] = 0.0;
     for (int e = 0; e < 3; ++e) ring_issue<NPOT>(c, e, nent);
+    const double nqi = act ? -c.sQi()[lane] : 0.0;           // Y2[r][k] = -A2[r][k] inv(2Q)[k]
+    const double *a2c = c.sA2() + (lane < NPOT ? lane : 0);  // column `lane` of A2
     double acc = 0.0, yi = 0.0;
     for (int e = 0; e < nent; ++e) {
-        const int i = NB - 1 - e / 3, kind = e % 3;
-        if (kind == 0) yi = act ? c.YV()[(size_t)i * npad + lane] : 0.0;       // consumed two entries later
+        const int i = NB - 1 - e / 2, kind = e % 2;
+        if (kind == 0) yi = act ? c.YV()[(size_t)i * npad + lane] : 0.0;       // consumed one entry later
         cp_async_wait<2>();
         __syncwarp();
         const double *M = c.wsm + (e % 3) * (NPOT * NPOT) + (lane < NPOT ? lane : 0);
-        if (kind < 2) {
-            if (kind == 0) acc = 0.0;
-            const bool on = (kind == 0) ? (i + 1 < NB) : (i + 2 < NB && c.a2);
-            if (on) {
-                const double *dv = vec + ((i + 1 + kind) % 3) * 32;
+        if (kind == 0) {
+            acc = 0.0;
+            if (i + 1 < NB) {                                 // L1_i' dnu_{i+1}
+                const double *dv = vec + ((i + 1) % 3) * 32;
                 double mv[NPOT];
 #pragma unroll
                 for (int r = 0; r < NPOT; ++r) mv[r] = M[r * NPOT];
@@ -1248,8 +1248,23 @@ __device__ __forceinline__ void backward_sweep(const WCtx &c)
                 for (int r = 0; r < NPOT; ++r) s[r & 3] = fma(mv[r], dv[r], s[r & 3]);
                 acc += (s[0] + s[1]) + (s[2] + s[3]);
             }
+            if (i + 2 < NB && c.a2 && c.y2i[i] >= 0) {        // w = Y2' dnu_{i+2} (shared-memory constants), consumed with inv(L_i)
+                const double *dv = vec + ((i + 2) % 3) * 32;
+                double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int r = 0; r < NPOT; ++r) s[r & 3] = fma(a2c[r * LD], dv[r], s[r & 3]);
+                vec[128 + lane] = act ? nqi * ((s[0] + s[1]) + (s[2] + s[3])) : 0.0;
+            } else {
+                vec[128 + lane] = 0.0;
+            }
         } else {
             double *tmp = vec + 96;
+            const double *w2 = vec + 128;
+            const double *Mr = c.wsm + (e % 3) * (NPOT * NPOT) + (lane < NPOT ? lane : 0) * NPOT;      // row `lane` of inv(L_i)
+            double s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < NPOT; ++r) s2[r & 3] = fma(Mr[r], w2[r], s2[r & 3]);                    // (inv(L_i) w)[lane]
+            acc += (s2[0] + s2[1]) + (s2[2] + s2[3]);
             double mv[NPOT];
 #pragma unroll
             for (int r = 0; r < NPOT; ++r) mv[r] = M[r * NPOT];
