@@ -16,4 +16,4 @@ $S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k 
 # general-structure kernel after the round-2 rewrite: both block sizes, n > 32 (shared-memory potrf), dense R, chunked panel (n = 100)
 $S --tool memcheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s301 or s304 or s306 or s308 or s309 or s310 or cold_start or s401 or s403" 2>&1 | tail -4
 $S --tool racecheck python -m pytest tests/test_gpu_fmpc_gen.py -m gpu -x -q -k "s310 or s305 or s304 or s401" 2>&1 | tail -4
-$S --tool memcheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "72 or no_size_limit or larger" 2>&1 | tail -4
+$S --tool memcheck python -m pytest tests/test_gpu_fmpc.py -m gpu -x -q -k "large_state_dimension" 2>&1 | tail -4
