@@ -766,9 +766,12 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 PB_T(4);
                 // -- phase 3: L1_i = M1 inv(L)' (in place), L2_i = Y2 inv(L)' (into the dead L2pp block), y_i = inv(L) rhs --
                 double *bM2 = bL2pp;
-                for (int rt = wid; rt < nt; rt += NWARPS) {
+                // 2 nt tasks (product, row tile) instead of nt (row tile, both products): nt = 9 row tiles on 8 warps left seven warps waiting
+                // for the one with two tasks
+                for (int task = wid; task < 2 * nt; task += NWARPS) {
+                    const int rt = task % nt, which = task / nt;
                     const int r = 8 * rt + gq;
-                    if (has1) {
+                    if (which == 0 && has1) {
                         double af[KSMAX];
 #pragma unroll
                         for (int k = 0; k < KSMAX; ++k) af[k] = (k < ks) ? bM1[r * ld + 4 * k + q] : 0.0;
@@ -789,7 +792,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                             }
                         }
                     }
-                    if (has2) {
+                    if (which == 1 && has2) {
                         const int y2 = S.y2i[i];
                         double af[KSMAX];
 #pragma unroll
@@ -812,7 +815,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                                 if (cc + 1 < n) gL2[(size_t)i * nn + r * n + cc + 1] = c1;
                             }
                         }
-                    } else {
+                    } else if (which == 1) {
                         // the block held the U scratch of the factorization: restore the zero padding invariant
                         for (int ct = 0; ct < nt; ++ct) {
                             const int cc = 8 * ct + 2 * q;
