@@ -301,14 +301,17 @@ __device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, in
     const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5, gq = lane >> 2, q = lane & 3;
     const int nt = RP / 8;
     double *wtmp = tmp + 128 + 64 * wid;                // per-warp 8 x 8 scratch; tmp[0..127]: inv(L_kk), double buffered
-    if (tid == 0) *s_info = 0;
+    // s_info[2]: the failure flag of the diagonal tile kb + 1 goes to slot (kb + 1) & 1, so that the write of one step cannot race with
+    // the threads still reading the flag of the step before (racecheck: WAR on a single flag; an early return of a few threads
+    // would have shifted the barriers of the failure path)
+    if (tid == 0) { s_info[0] = 0; s_info[1] = 0; }
     __syncthreads();
     if (wid == 0) {
         const int info = diag_tile_potrf_inverse(bS, bT, ld, n, 0, tmp, lane);
-        if (info && lane == 0) *s_info = info;
+        if (info && lane == 0) s_info[0] = info;
     }
     __syncthreads();
-    if (*s_info) return *s_info;
+    if (s_info[0]) return s_info[0];
     for (int kb = 0; kb + 1 < nt; ++kb) {
         const double *tLi = tmp + 64 * (kb & 1);
         const int R = nt - kb - 1, ntask = R * (R + 1) / 2;
@@ -344,12 +347,12 @@ __device__ __noinline__ int cta_potrf_inverse(double *bS, double *bT, int ld, in
             tile_task(0);                                        // (kb+1, kb+1): the next diagonal tile ...
             __syncwarp();
             const int info = diag_tile_potrf_inverse(bS, bT, ld, n, kb + 1, tmp + 64 * ((kb + 1) & 1), lane);   // ... factored at once
-            if (info && lane == 0) *s_info = info;
+            if (info && lane == 0) s_info[(kb + 1) & 1] = info;
         } else {
             for (int task = wid; task < ntask; task += nw - 1) tile_task(task);
         }
         __syncthreads();
-        if (*s_info) return *s_info;
+        if (s_info[(kb + 1) & 1]) return s_info[(kb + 1) & 1];
     }
     // ---- inv(L) by block columns: column k is an independent forward substitution over its block rows, one warp per
     //      column and no CTA barrier inside (L[i,j] is read from the mirrored tile (j, i)) ----
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
     double *colbuf = sm_y2 + VL;                            // 64
     double *rsv = colbuf + 64;                              // VL
     double *red = rsv + VL;                                 // 36
-    __shared__ int s_inst, s_flag, s_info2;
+    __shared__ int s_inst, s_flag, s_info2[2];
     double *ptmp = red + 36;                                // potrf scratch (n > 32): 64 + 64 per warp
     const KC kc{S, n, m, T, NB, A.has_xf, tid, lane, wid, gq, q, ld, nt, ks, mp, ldp, TP, G.ntt, Us, Xs, red, NTHREADS, NWARPS};
 
@@ -752,7 +755,7 @@ __global__ void __launch_bounds__(KCfg<NP>::NTH, KCfg<NP>::MINB) fmpc_solve_kern
                 PB_T(3);
                 // -- phase 2: factor + invert the diagonal block (one warp, rotating over the SM sub-partitions) --
                 if constexpr (NP > 32) {
-                    const int info = cta_potrf_inverse(bS, bL2pp, ld, RP, gLi + (size_t)i * nn, n, tid, NTHREADS, ptmp, &s_info2);
+                    const int info = cta_potrf_inverse(bS, bL2pp, ld, RP, gLi + (size_t)i * nn, n, tid, NTHREADS, ptmp, s_info2);
                     __syncthreads();
                     if (tid == 0) s_flag = info;
                 } else {
