@@ -176,8 +176,8 @@ struct WsW {
         L.tu = (size_t)g.TP8 * g.mpad;                 // UC UT HU HUT HDU DU WV DB RDU
         L.tx = (size_t)g.TP8 * g.npad;                 // XC XT HX HXT HDX DX RDX
         L.tb = (size_t)(g.TP8 + 1) * g.npad;           // RP RPT YV DNU BV
-        L.bl = (size_t)(g.T + 1) * g.NN;               // inv(L), L1, L2  (row-major, leading dimension NPOT)
-        L.total = (9 * L.tu + 7 * L.tx + 5 * L.tb + 3 * L.bl + 31) & ~(size_t)31;
+        L.bl = (size_t)(g.T + 1) * g.NN;               // inv(L), L1  (row-major, leading dimension NPOT; L2 is rebuilt by the backward sweep)
+        L.total = (9 * L.tu + 7 * L.tx + 5 * L.tb + 2 * L.bl + 31) & ~(size_t)31;
         return L;
     }
 };
