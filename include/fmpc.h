@@ -257,11 +257,12 @@ long long fmpc_launch_count(const fmpc_handle *h);
 long long fmpc_last_newton_iters(fmpc_handle *h);
 /* Which solve kernel the handle selected: 2 = warp-per-instance DMMA kernel (n <= 32), 1 = CTA-per-instance
  * DMMA kernel (32 < n <= 72), 0 = scalar reference kernel (only when forced), 3 = general-structure kernel (VAR_1 ramp rows, literal
- * VAR_1 columns, dense Q / Qf). */
+ * VAR_1 columns, dense Q / Qf, dense R, n > 72). */
 int fmpc_kernel_kind(const fmpc_handle *h);
 /* Phase cycle counters of the last solve launch, summed over warps (all zero unless the library was
- * built with -DFMPC_PROF): init, newton pass, forward sweep, backward sweep, C' pass, line search,
- * accept, copy-out, 4 spare. */
+ * built with -DFMPC_PROF): warp kernel: init, newton pass, forward sweep, backward sweep, C' pass, line search,
+ * accept, copy-out, 4 spare; general-structure kernel (thread 0 of every CTA): init, barrier + residuals, inv(Phi_uu), rhs,
+ * Schur assembly, potrf + staging, panel, trailing update, backward substitution, dz, line search, copy-out. */
 int fmpc_last_profile(fmpc_handle *h, long long *out12);
 
 const char *fmpc_strerror(int code);
